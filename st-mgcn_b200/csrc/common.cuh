@@ -1,0 +1,65 @@
+// Shared host/device helpers for libstmgcn_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/stmgcn_b200.h"
+
+namespace stmgcn {
+
+// ---- error reporting across the C boundary (no exceptions; thread-local message) -------------------
+void set_error(const char* fmt, ...);
+int32_t fail(int32_t code, const char* fmt, ...);
+int32_t check_launch(const char* what);        // cudaGetLastError() only -- never synchronises
+void count_launch(int n = 1);
+int sm_count();
+
+#define STMGCN_REQUIRE(cond, code, ...)                                   \
+    do {                                                                  \
+        if (!(cond)) return ::stmgcn::fail((code), __VA_ARGS__);          \
+    } while (0)
+
+#define STMGCN_CUDA(expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return ::stmgcn::fail((int32_t)_e, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
+// tanh via exp: accurate to ~1e-7 relative on the range the LSTM sees; saturates correctly.
+__device__ __forceinline__ float tanhf_(float v) {
+    float a = fabsf(v);
+    float e = __expf(-2.0f * a);
+    float r = (1.0f - e) / (1.0f + e);
+    return copysignf(r, v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// streaming (read-once) 128-bit load that does not pollute L1
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+}  // namespace stmgcn

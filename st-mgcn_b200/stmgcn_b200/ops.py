@@ -1,0 +1,371 @@
+"""``torch.autograd.Function`` wrappers around the C ABI -- host plumbing only.
+
+Every tensor the kernels touch is allocated here through torch's caching allocator on the current stream
+(the library never allocates per call, SURVEY.md section 8(b) "ownership").  All feature tensors are fp32
+"node-major": ``(N, B, p)`` contiguous, rows ``r = n*B + b``.
+
+Functions (reference lines they replace):
+  ObsToNodeMajor   STMGCN.py:36,39 (sum over C, permute) and :47 (row order of the shared LSTM)
+  ChebGCN          GCN.py:24-43 on a sparse L~ (recurrence on features) -> out (N,B,q)
+  TemporalPool     STMGCN.py:40-42: GCN over time-as-features + residual + sum over regions -> (B,T)
+  ContextGate      STMGCN.py:42-43: /N, fc, relu, fc (same weights), sigmoid -> s (B,T)
+  SharedLSTM       STMGCN.py:44,47-50: modulate + 3-layer shared LSTM, one library call per timestep
+  FuseOut          STMGCN.py:116-118: sum over graphs + output FC -> (B,N,C)
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .graph import SupportSet
+
+L = _lib.lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("stmgcn_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+# --------------------------------------------------------------------------------------------------
+# raw helpers (no autograd)
+# --------------------------------------------------------------------------------------------------
+def spmm_step(g, transpose: bool, alpha: float, x: torch.Tensor, beta: float, z: Optional[torch.Tensor],
+              gamma: float, u: Optional[torch.Tensor], y: torch.Tensor) -> None:
+    """``y = alpha * op(A) x + beta * z + gamma * u`` on ``(N, F)`` views."""
+    n = g.n
+    f_total = x.numel() // n
+    _lib.check(L.stmgcn_cheb_spmm_step(g.ptr, int(transpose), alpha, x.data_ptr(), beta, _p(z), gamma, _p(u),
+                                       y.data_ptr(), f_total, _stream()), "cheb_spmm_step")
+
+
+def cheb_stack_(sset: SupportSet, s: torch.Tensor) -> None:
+    """Fill ``s[1:]`` from ``s[0]``;  s: (Ks, N, B, p)."""
+    ks = sset.ks
+    if sset.mode == "cheb":
+        if ks > 1:
+            g = sset.graphs[0]
+            spmm_step(g, False, 1.0, s[0], 0.0, None, 0.0, None, s[1])
+            for k in range(2, ks):
+                spmm_step(g, False, 2.0, s[k - 1], -1.0, s[k - 2], 0.0, None, s[k])
+    else:
+        raise AssertionError("generic supports are stacked by cheb_stack_generic")
+
+
+def cheb_stack_generic(sset: SupportSet, x: torch.Tensor) -> torch.Tensor:
+    """Generic supports: S_k = A_k x for every k (including k = 0)."""
+    s = torch.empty((sset.ks,) + tuple(x.shape), device=x.device, dtype=torch.float32)
+    for k in range(sset.ks):
+        spmm_step(sset.graphs[k], False, 1.0, x, 0.0, None, 0.0, None, s[k])
+    return s
+
+
+def build_stack(sset: SupportSet, x: torch.Tensor) -> torch.Tensor:
+    if sset.mode == "cheb":
+        s = torch.empty((sset.ks,) + tuple(x.shape), device=x.device, dtype=torch.float32)
+        s[0].copy_(x)
+        cheb_stack_(sset, s)
+        return s
+    return cheb_stack_generic(sset, x)
+
+
+def adjoint_stack_(sset: SupportSet, u: torch.Tensor) -> torch.Tensor:
+    """Given U_k = dZ W_k^T stacked in ``u`` (Ks, N, B, p) return dX (N, B, p); ``u`` is clobbered.
+
+    cheb: adjoint Clenshaw with L~^T; generic: sum_k A_k^T U_k.
+    """
+    ks = sset.ks
+    if sset.mode == "cheb":
+        if ks == 1:
+            return u[0]
+        g = sset.graphs[0]
+        k_ord = ks - 1
+        # b_K = U_K (in place).  b_k = U_k + 2 L^T b_{k+1} - b_{k+2}  written over U_k.
+        for k in range(k_ord - 1, 0, -1):
+            z = u[k + 2] if k + 2 <= k_ord else None
+            spmm_step(g, True, 2.0, u[k + 1], -1.0 if z is not None else 0.0, z, 1.0, u[k], u[k])
+        z = u[2] if k_ord >= 2 else None
+        spmm_step(g, True, 1.0, u[1], -1.0 if z is not None else 0.0, z, 1.0, u[0], u[0])
+        return u[0]
+    out = torch.empty_like(u[0])
+    acc = None
+    for k in range(ks):
+        tgt = out if (k % 2 == 0) else torch.empty_like(out)
+        spmm_step(sset.graphs[k], True, 1.0, u[k], 0.0, None, 1.0 if acc is not None else 0.0, acc, tgt)
+        acc = tgt
+    return acc
+
+
+def _proj_fwd(s: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int, pool: Optional[torch.Tensor],
+              b_inner: int) -> torch.Tensor:
+    ks, n, b, p = s.shape
+    q = w.shape[1]
+    out = torch.empty((n, b, q), device=s.device, dtype=torch.float32)
+    _lib.check(L.stmgcn_proj_fwd(s.data_ptr(), n * b * p, ks, n * b, p, w.data_ptr(), _p(bias), q, act,
+                                 out.data_ptr(), _p(pool), b_inner, _stream()), "proj_fwd")
+    return out
+
+
+def _proj_bwd(s: torch.Tensor, w: torch.Tensor, act: int, out: torch.Tensor, d_out: Optional[torch.Tensor],
+              d_bcast: Optional[torch.Tensor], scale: float, b_inner: int, need_bias: bool, need_u: bool):
+    ks, n, b, p = s.shape
+    q = w.shape[1]
+    dw = torch.zeros_like(w, dtype=torch.float32)
+    db = torch.zeros(q, device=s.device, dtype=torch.float32) if need_bias else None
+    dz = torch.empty((n * b, q), device=s.device, dtype=torch.float32)
+    u = torch.empty_like(s) if need_u else None
+    wt = w.t().contiguous() if need_u else None
+    _lib.check(L.stmgcn_proj_bwd(s.data_ptr(), n * b * p, ks, n * b, p, _p(wt), q, act, out.data_ptr(), _p(d_out),
+                                 _p(d_bcast), scale, b_inner, dz.data_ptr(), dw.data_ptr(), _p(db), _p(u),
+                                 n * b * p, _stream()), "proj_bwd")
+    return dw, db, u
+
+
+# --------------------------------------------------------------------------------------------------
+# autograd Functions
+# --------------------------------------------------------------------------------------------------
+def obs_to_node_major(obs: torch.Tensor):
+    """obs (B,T,N,C) -> xo (N,B,T,C), xt (N,B,T).  Observations are data: no gradient flows back."""
+    _require_cuda(obs)
+    if obs.requires_grad:
+        raise NotImplementedError("stmgcn_b200 treats obs_seq as data; gradients w.r.t. obs_seq are not provided")
+    obs = _f32c(obs.detach())
+    b, t, n, c = obs.shape
+    xt = torch.empty((n, b, t), device=obs.device, dtype=torch.float32)
+    xo = torch.empty((n, b, t, c), device=obs.device, dtype=torch.float32) if c > 1 else None
+    _lib.check(L.stmgcn_obs_to_node_major(obs.data_ptr(), _p(xo), xt.data_ptr(), b, t, n, c, _stream()),
+               "obs_to_node_major")
+    return (xo if xo is not None else xt.view(n, b, t, 1)), xt
+
+
+class ChebGCN(torch.autograd.Function):
+    """out (N,B,q) = act( sum_k (T_k x) W_k + b ),  x (N,B,p) node-major."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, sset: SupportSet, act: int):
+        _require_cuda(x, w)
+        x, w = _f32c(x), _f32c(w)
+        bias_c = _f32c(bias) if bias is not None else None
+        s = build_stack(sset, x)
+        out = _proj_fwd(s, w, bias_c, act, None, x.shape[1])
+        ctx.sset, ctx.act, ctx.has_bias = sset, act, bias is not None
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(s, w, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        s, w, out = ctx.saved_tensors
+        need_dx = ctx.needs_input_grad[0]
+        d_out = _f32c(d_out)
+        dw, db, u = _proj_bwd(s, w, ctx.act, out, d_out, None, 1.0, s.shape[2], ctx.has_bias, need_dx)
+        dx = adjoint_stack_(ctx.sset, u) if need_dx else None
+        return dx, dw, db, None, None
+
+
+class TemporalPool(torch.autograd.Function):
+    """pool (B,T) = sum_n ( x + act(GCN_T(x)) )[n,b,:]  (STMGCN.py:40-42 before the division by N).
+    x is data (no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, sset: SupportSet, act: int):
+        _require_cuda(x, w)
+        x, w = _f32c(x), _f32c(w)
+        bias_c = _f32c(bias) if bias is not None else None
+        n, b, t = x.shape
+        if w.shape[1] != t:
+            raise ValueError("temporal GCN must map seq_len -> seq_len")
+        s = build_stack(sset, x)
+        pool = torch.zeros((b, t), device=x.device, dtype=torch.float32)
+        out = _proj_fwd(s, w, bias_c, act, pool, b)
+        ctx.act, ctx.has_bias = act, bias is not None
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(s, w, out)
+        return pool
+
+    @staticmethod
+    def backward(ctx, d_pool):
+        s, w, out = ctx.saved_tensors
+        d_pool = _f32c(d_pool)
+        dw, db, _ = _proj_bwd(s, w, ctx.act, out, None, d_pool, 1.0, s.shape[2], ctx.has_bias, False)
+        return None, dw, db, None, None
+
+
+class ContextGate(torch.autograd.Function):
+    """s = sigmoid(fc(relu(fc(pool / N))))  -- the same fc twice (STMGCN.py:43)."""
+
+    @staticmethod
+    def forward(ctx, pool, fcw, fcb, n_regions: int):
+        _require_cuda(pool, fcw, fcb)
+        pool, fcw, fcb = _f32c(pool), _f32c(fcw), _f32c(fcb)
+        b, t = pool.shape
+        z, a1, s = (torch.empty_like(pool) for _ in range(3))
+        _lib.check(L.stmgcn_gate_fwd(pool.data_ptr(), b, t, n_regions, fcw.data_ptr(), fcb.data_ptr(),
+                                     z.data_ptr(), a1.data_ptr(), s.data_ptr(), _stream()), "gate_fwd")
+        ctx.n_regions = n_regions
+        ctx.save_for_backward(z, a1, s, fcw)
+        return s
+
+    @staticmethod
+    def backward(ctx, d_s):
+        z, a1, s, fcw = ctx.saved_tensors
+        d_s = _f32c(d_s)
+        b, t = s.shape
+        d_fcw = torch.zeros_like(fcw)
+        d_fcb = torch.zeros(t, device=s.device, dtype=torch.float32)
+        d_z = torch.empty_like(s)
+        _lib.check(L.stmgcn_gate_bwd(d_s.data_ptr(), z.data_ptr(), a1.data_ptr(), s.data_ptr(), b, t,
+                                     fcw.data_ptr(), d_fcw.data_ptr(), d_fcb.data_ptr(), d_z.data_ptr(),
+                                     _stream()), "gate_bwd")
+        return d_z / float(ctx.n_regions), d_fcw, d_fcb, None
+
+
+def _pack_lstm(weights: Sequence[torch.Tensor], n_layers: int, hid: int):
+    """nn.LSTM parameters -> packed operands (see include/stmgcn_b200.h)."""
+    w_ih0 = weights[0]
+    c_in = w_ih0.shape[1]
+    wx = w_ih0.reshape(4, hid, c_in).permute(2, 1, 0).reshape(c_in, 4 * hid).contiguous()
+    wp, bp, wpt = [], [], []
+    for l in range(n_layers):
+        w_ih, w_hh, b_ih, b_hh = weights[4 * l:4 * l + 4]
+        cat = w_hh if l == 0 else torch.cat([w_ih, w_hh], dim=1)
+        kd = cat.shape[1]
+        packed = cat.reshape(4, hid, kd).permute(2, 1, 0).reshape(kd, 4 * hid).contiguous()
+        wp.append(packed)
+        wpt.append(packed.t().contiguous())
+        bp.append((b_ih + b_hh).reshape(4, hid).t().reshape(4 * hid).contiguous())
+    return wx, wp, bp, wpt
+
+
+def _unpack_lstm_grads(dwx, dwp, dbp, n_layers: int, hid: int, c_in: int):
+    grads = []
+    for l in range(n_layers):
+        kd = dwp[l].shape[0]
+        full = dwp[l].reshape(kd, hid, 4).permute(2, 1, 0).reshape(4 * hid, kd)
+        if l == 0:
+            d_ih = dwx.reshape(c_in, hid, 4).permute(2, 1, 0).reshape(4 * hid, c_in).contiguous()
+            d_hh = full.contiguous()
+        else:
+            d_ih, d_hh = full[:, :hid].contiguous(), full[:, hid:].contiguous()
+        d_b = dbp[l].reshape(hid, 4).t().reshape(4 * hid).contiguous()
+        grads += [d_ih, d_hh, d_b, d_b.clone()]
+    return grads
+
+
+class SharedLSTM(torch.autograd.Function):
+    """h_top (N,B,H) of the shared multi-layer LSTM over rows r = n*B + b; input ``xo * s[b,t]``.
+
+    forward(xo (N,B,T,C), s (B,T), h0|None, c0|None (L,R,H), n_layers, hid, *lstm_weights) where
+    lstm_weights = [w_ih_l0, w_hh_l0, b_ih_l0, b_hh_l0, w_ih_l1, ...] (nn.LSTM names/shapes).
+    Returns (h_top, h_n (L,R,H), c_n (L,R,H)); the last two are not differentiable.
+    """
+
+    @staticmethod
+    def forward(ctx, xo, s_gate, h0, c0, n_layers: int, hid: int, *weights):
+        _require_cuda(xo, s_gate, *weights)
+        xo, s_gate = _f32c(xo), _f32c(s_gate)
+        weights = [_f32c(w) for w in weights]
+        n, b, t_len, c_in = xo.shape
+        rows = n * b
+        dev = xo.device
+        h0c = _f32c(h0) if h0 is not None else None
+        c0c = _f32c(c0) if c0 is not None else None
+        need_grad = any(ctx.needs_input_grad)
+        wx, wp, bp, wpt = _pack_lstm(weights, n_layers, hid)
+        hs = torch.empty((n_layers, t_len, rows, hid), device=dev, dtype=torch.float32)
+        cs = torch.empty((n_layers, t_len, rows, hid), device=dev, dtype=torch.float32)
+        gates = torch.empty((n_layers, t_len, rows, 4 * hid), device=dev, dtype=torch.float32) if need_grad else None
+        wp_arr, bp_arr = _lib.ptr_array([w.data_ptr() for w in wp]), _lib.ptr_array([v.data_ptr() for v in bp])
+        st = _stream()
+        for t in range(t_len):
+            _lib.check(L.stmgcn_lstm_step_fwd(t, t_len, n_layers, rows, hid, c_in, b, xo.data_ptr(),
+                                              s_gate.data_ptr(), wx.data_ptr(), wp_arr, bp_arr, _p(h0c), _p(c0c),
+                                              hs.data_ptr(), cs.data_ptr(), _p(gates), st), "lstm_step_fwd")
+        ctx.dims = (n, b, t_len, c_in, n_layers, hid)
+        if need_grad:
+            ctx.save_for_backward(xo, s_gate, h0c, c0c, hs, cs, gates, wx, *wpt)
+        h_top = hs[n_layers - 1, t_len - 1].view(n, b, hid)
+        h_n, c_n = hs[:, t_len - 1], cs[:, t_len - 1]
+        ctx.mark_non_differentiable(h_n, c_n)
+        return h_top, h_n, c_n
+
+    @staticmethod
+    def backward(ctx, d_top, _dhn, _dcn):
+        xo, s_gate, h0, c0, hs, cs, gates, wx, *wpt = ctx.saved_tensors
+        n, b, t_len, c_in, n_layers, hid = ctx.dims
+        rows = n * b
+        dev = xo.device
+        d_top = _f32c(d_top).view(rows, hid)
+        dh_rec = torch.zeros((n_layers, rows, hid), device=dev, dtype=torch.float32)
+        dc = torch.zeros((n_layers, rows, hid), device=dev, dtype=torch.float32)
+        dx_work = torch.empty((rows, hid), device=dev, dtype=torch.float32)
+        d_s = torch.zeros((b, t_len), device=dev, dtype=torch.float32)
+        dwx = torch.zeros_like(wx)
+        dbp = [torch.zeros(4 * hid, device=dev, dtype=torch.float32) for _ in range(n_layers)]
+        dwp = [torch.zeros((w.shape[1], 4 * hid), device=dev, dtype=torch.float32) for w in wpt]
+        wpt_arr = _lib.ptr_array([w.data_ptr() for w in wpt])
+        dbp_arr = _lib.ptr_array([v.data_ptr() for v in dbp])
+        st = _stream()
+        # NOTE: gates is overwritten in place with dA (the tape is consumed; double backward unsupported)
+        for t in range(t_len - 1, -1, -1):
+            _lib.check(L.stmgcn_lstm_step_bwd(t, t_len, n_layers, rows, hid, c_in, b, xo.data_ptr(),
+                                              s_gate.data_ptr(), wx.data_ptr(), wpt_arr, _p(c0), cs.data_ptr(),
+                                              gates.data_ptr(), d_top.data_ptr(), dh_rec.data_ptr(),
+                                              dc.data_ptr(), dx_work.data_ptr(), d_s.data_ptr(), dwx.data_ptr(),
+                                              dbp_arr, st), "lstm_step_bwd")
+        for l in range(n_layers):
+            _lib.check(L.stmgcn_lstm_wgrad(l, t_len, n_layers, rows, hid, _p(h0), hs.data_ptr(), gates.data_ptr(),
+                                           dwp[l].data_ptr(), st), "lstm_wgrad")
+        w_grads = _unpack_lstm_grads(dwx, dwp, dbp, n_layers, hid, c_in)
+        return (None, d_s, None, None, None, None, *w_grads)
+
+
+class FuseOut(torch.autograd.Function):
+    """y (B,N,C) = fc( sum_m g_m ),  g_m (N,B,G) node-major  (STMGCN.py:116-118)."""
+
+    @staticmethod
+    def forward(ctx, fcw, fcb, *gs):
+        _require_cuda(fcw, fcb, *gs)
+        fcw, fcb = _f32c(fcw), _f32c(fcb)
+        gs = [_f32c(g) for g in gs]
+        n, b, gdim = gs[0].shape
+        c = fcw.shape[0]
+        feat = torch.empty_like(gs[0])
+        y = torch.empty((b, n, c), device=feat.device, dtype=torch.float32)
+        arr = _lib.ptr_array([g.data_ptr() for g in gs])
+        _lib.check(L.stmgcn_fuse_out_fwd(arr, len(gs), n, b, gdim, c, fcw.data_ptr(), fcb.data_ptr(),
+                                         feat.data_ptr(), y.data_ptr(), _stream()), "fuse_out_fwd")
+        ctx.m = len(gs)
+        ctx.save_for_backward(feat, fcw)
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        feat, fcw = ctx.saved_tensors
+        d_y = _f32c(d_y)
+        n, b, gdim = feat.shape
+        c = fcw.shape[0]
+        d_feat = torch.empty_like(feat)
+        d_fcw = torch.zeros_like(fcw)
+        d_fcb = torch.zeros(c, device=feat.device, dtype=torch.float32)
+        _lib.check(L.stmgcn_fuse_out_bwd(d_y.data_ptr(), feat.data_ptr(), n, b, gdim, c, fcw.data_ptr(),
+                                         d_feat.data_ptr(), d_fcw.data_ptr(), d_fcb.data_ptr(), _stream()),
+                   "fuse_out_bwd")
+        return (d_fcw, d_fcb) + tuple(d_feat for _ in range(ctx.m))

@@ -1,0 +1,194 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the drop-in modules) against the oracle and the
+golden vectors generated from the reference.  Tolerance: 1e-4 max-norm relative (BASELINE.json)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+from torch import nn
+
+import stmgcn_oracle as O
+from helpers import TOL, assert_close, build_model, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand_csr(n, density, seed, asym=True):
+    rng = np.random.default_rng(seed)
+    a = (rng.random((n, n)) < density) * rng.standard_normal((n, n))
+    if not asym:
+        a = (a + a.T) / 2
+    a[np.arange(n), (np.arange(n) + 1) % n] = 0.5          # no empty rows
+    return a.astype(np.float32)
+
+
+def test_graph_handle_roundtrip():
+    from stmgcn_b200.graph import GraphHandle
+    a = _rand_csr(97, 0.1, 0)
+    g = GraphHandle.from_dense(torch.from_numpy(a).to(DEV))
+    ref = sp.csr_matrix(a)
+    assert g.n == 97 and g.nnz == ref.nnz
+    rp, ci, va = [t.cpu().numpy() for t in g.export(False)]
+    assert np.array_equal(rp, ref.indptr) and np.array_equal(ci, ref.indices) and np.array_equal(va, ref.data)
+    ref_t = sp.csr_matrix(a.T)
+    rp, ci, va = [t.cpu().numpy() for t in g.export(True)]
+    assert np.array_equal(rp, ref_t.indptr) and np.array_equal(ci, ref_t.indices) and np.array_equal(va, ref_t.data)
+    # CSR entry == dense entry
+    g2 = GraphHandle.from_csr(97, torch.from_numpy(ref.indptr).to(DEV), torch.from_numpy(ref.indices).to(DEV),
+                              torch.from_numpy(ref.data).to(DEV))
+    rp2, ci2, va2 = [t.cpu().numpy() for t in g2.export(True)]
+    assert np.array_equal(rp2, ref_t.indptr) and np.array_equal(ci2, ref_t.indices) and np.array_equal(va2, ref_t.data)
+
+
+@pytest.mark.parametrize("n,f", [(64, 32), (97, 7), (300, 768), (128, 132), (1, 4)])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_spmm_step(n, f, transpose):
+    from stmgcn_b200 import ops
+    from stmgcn_b200.graph import GraphHandle
+    a = _rand_csr(n, 0.08, n + f)
+    g = GraphHandle.from_dense(torch.from_numpy(a).to(DEV))
+    rng = np.random.default_rng(1)
+    x, z, u = (rng.standard_normal((n, f)).astype(np.float32) for _ in range(3))
+    xd, zd, ud = (torch.from_numpy(v).to(DEV) for v in (x, z, u))
+    y = torch.empty_like(xd)
+    op = a.T if transpose else a
+    ops.spmm_step(g, transpose, 2.0, xd, -1.0, zd, 0.5, ud, y)
+    ref = 2.0 * (op.astype(np.float64) @ x) - z + 0.5 * u
+    assert_close(y.cpu().numpy(), ref, "spmm full", 1e-5)
+    ops.spmm_step(g, transpose, 1.0, xd, 0.0, None, 0.0, None, y)
+    assert_close(y.cpu().numpy(), op.astype(np.float64) @ x, "spmm plain", 1e-5)
+    # in-place on the U operand (used by the adjoint Clenshaw)
+    ops.spmm_step(g, transpose, 2.0, xd, -1.0, zd, 1.0, ud, ud)
+    assert_close(ud.cpu().numpy(), 2.0 * (op.astype(np.float64) @ x) - z + u, "spmm in-place", 1e-5)
+
+
+@pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref"])
+def test_model_matches_reference_golden(name):
+    """Forward output, loss and EVERY parameter gradient vs vectors produced by the unmodified reference."""
+    meta, params, grads, supports, _, blob = load_golden(name)
+    model = build_model(meta, DEV)
+    model.load_state_dict(params)
+    x = torch.from_numpy(blob["x"]).to(DEV)
+    y = torch.from_numpy(blob["y"]).to(DEV)
+    sups = [s.to(DEV) for s in supports]
+    out = model(obs_seq=x, sta_adj_list=sups)
+    loss = nn.MSELoss(reduction="mean")(out, y)
+    loss.backward()
+    assert_close(out.detach().cpu().numpy(), blob["out"], f"{name} forward")
+    assert abs(loss.item() - float(blob["loss"])) <= 1e-5 * max(1.0, abs(float(blob["loss"])))
+    for key, p in model.named_parameters():
+        assert p.grad is not None, key
+        assert_close(p.grad.cpu().numpy(), grads[key], f"{name} grad {key}")
+    # inference mode (Model_Trainer.py:33 set_grad_enabled(False)) gives the same output
+    with torch.no_grad():
+        out2 = model(obs_seq=x, sta_adj_list=sups)
+    assert_close(out2.cpu().numpy(), blob["out"], f"{name} no_grad forward")
+
+
+def _mid_case(n, m, k, t, b, c, hid, layers, gcn_hid, seed, dens=0.05):
+    from stmgcn_b200 import synth
+    adjs = [synth.make_adjacency(n, g, dens) for g in range(m)]
+    gen = torch.Generator().manual_seed(seed)
+    adjs = [a * (0.5 + torch.rand(n, n, generator=gen)) for a in adjs]          # weighted, asymmetric
+    sups = [O.chebyshev_supports_dense(a, k, lambda_max=1.7) for a in adjs]     # non-unit diagonal in L~
+    params = O.init_params(m, t, c, hid, layers, gcn_hid, k + 1, seed=seed)
+    x = torch.randn(b, t, n, c, generator=gen)
+    y = torch.randn(b, n, c, generator=gen)
+    return sups, params, x, y
+
+
+@pytest.mark.parametrize("shape", [
+    dict(n=256, m=3, k=3, t=12, b=8, c=1, hid=64, layers=3, gcn_hid=64),      # cfg2/3 shapes, small N/B
+    dict(n=130, m=2, k=5, t=24, b=3, c=1, hid=64, layers=3, gcn_hid=64),      # cfg5 shapes, ragged N
+    dict(n=65, m=1, k=0, t=1, b=1, c=3, hid=32, layers=1, gcn_hid=20),        # K=0, T=1, B=1
+    dict(n=50, m=2, k=2, t=7, b=5, c=2, hid=128, layers=2, gcn_hid=68),       # H=128 (two column panels)
+])
+def test_model_matches_sparse_oracle(shape):
+    """fwd + bwd vs the fp64 sparse oracle (itself pinned to the reference in tests/test_oracle.py)."""
+    from helpers import build_model
+    sups, params, x, y = _mid_case(seed=3, **shape)
+    model = build_model(shape, DEV)
+    model.load_state_dict(params)
+    out = model(obs_seq=x.to(DEV), sta_adj_list=[s.to(DEV) for s in sups])
+    loss = nn.MSELoss()(out, y.to(DEV))
+    loss.backward()
+    orc = O.SparseOracle({k_: v.numpy() for k_, v in params.items()},
+                         [O.laplacian_csr_from_supports(s) for s in sups], shape["k"] + 1, dtype=np.float64)
+    o_ref, l_ref, g_ref = orc.loss_and_grads(x.numpy(), y.numpy())
+    assert_close(out.detach().cpu().numpy(), o_ref, "forward")
+    assert abs(loss.item() - l_ref) <= 1e-5 * max(1.0, abs(l_ref))
+    for key, p in model.named_parameters():
+        assert_close(p.grad.cpu().numpy(), g_ref[key], f"grad {key}")
+
+
+def test_gcn_generic_supports_and_no_activation():
+    """localpool-style supports (A[0] != I) take the generic path; activation=None; x with odd strides."""
+    import GCN
+    n, b, p, q = 70, 4, 6, 10
+    adj = torch.from_numpy((_rand_csr(n, 0.1, 5, asym=False) != 0).astype(np.float32))
+    adj.fill_diagonal_(0)
+    sup = GCN.Adj_Preprocessor("localpool", 1).process(adj)
+    assert sup.shape == (1, n, n)
+    torch.manual_seed(0)
+    layer = GCN.GCN(K=1, input_dim=p, hidden_dim=q, bias=True, activation=None).to(DEV)
+    x = torch.randn(b, p, n).permute(0, 2, 1)                      # non-contiguous (B,N,p) view
+    xd = x.to(DEV).requires_grad_(True)
+    out = layer(sup.to(DEV), xd)
+    ref_x = x.clone().requires_grad_(True)
+    w, bias = layer.W.detach().cpu(), layer.b.detach().cpu()
+    w.requires_grad_(True)
+    ref = O.dense_gcn(sup, ref_x, w, bias, relu=False)
+    assert_close(out.detach().cpu().numpy(), ref.detach().numpy(), "generic forward")
+    gsum = torch.randn(b, n, q)
+    (out * gsum.to(DEV)).sum().backward()
+    (ref * gsum).sum().backward()
+    assert_close(xd.grad.cpu().numpy(), ref_x.grad.numpy(), "generic dX")
+    assert_close(layer.W.grad.cpu().numpy(), w.grad.numpy(), "generic dW")
+
+
+def test_cg_lstm_with_initial_hidden_state():
+    import STMGCN
+    from stmgcn_b200 import synth
+    n, b, t, c, hid, lyr, k = 40, 3, 5, 1, 16, 2, 2
+    sup = O.chebyshev_supports_dense(synth.make_adjacency(n, 0, 0.2), k)
+    torch.manual_seed(4)
+    mod = STMGCN.CG_LSTM(seq_len=t, n_nodes=n, input_dim=c, lstm_hidden_dim=hid, lstm_num_layers=lyr, K=k + 1,
+                         gconv_use_bias=True).to(DEV)
+    obs = torch.randn(b, t, n, c)
+    h0, c0 = torch.randn(lyr, b * n, hid) * 0.3, torch.randn(lyr, b * n, hid) * 0.3
+    out, (hn, cn) = mod(sup.to(DEV), obs.to(DEV), (h0.to(DEV), c0.to(DEV)))
+    params = {"p." + k_: v.detach().cpu() for k_, v in mod.state_dict().items()}
+    ref, (hn_r, cn_r) = O.dense_cg_lstm(sup, obs, params, "p.", hidden=(h0, c0))
+    assert_close(out.detach().cpu().numpy(), ref.numpy(), "cg_lstm out")
+    assert_close(hn.detach().cpu().numpy(), hn_r.numpy(), "h_n")
+    assert_close(cn.detach().cpu().numpy(), cn_r.numpy(), "c_n")
+
+
+def test_sparse_native_supports_equal_dense():
+    """Adj_Preprocessor.process_sparse (no dense polynomials) gives the same forward as the dense stack."""
+    import GCN
+    from stmgcn_b200 import synth
+    meta = dict(n=200, m=2, k=3, t=6, b=4, c=1, hid=32, layers=2, gcn_hid=16)
+    adjs = [synth.make_adjacency(200, g, 0.05) for g in range(2)]
+    pre = GCN.Adj_Preprocessor("chebyshev", 3)
+    dense = [pre.process(a).to(DEV) for a in adjs]
+    sparse = [pre.process_sparse(a).to(DEV) for a in adjs]
+    torch.manual_seed(1)
+    model = build_model(meta, DEV)
+    x = torch.randn(4, 6, 200, 1, device=DEV)
+    with torch.no_grad():
+        a = model(obs_seq=x, sta_adj_list=dense)
+        b_ = model(obs_seq=x, sta_adj_list=sparse)
+    assert_close(b_.cpu().numpy(), a.cpu().numpy(), "sparse-native vs dense supports", 1e-5)
+
+
+def test_errors_are_loud():
+    import GCN
+    from stmgcn_b200 import ops
+    layer = GCN.GCN(K=2, input_dim=4, hidden_dim=4).to(DEV)
+    with pytest.raises(RuntimeError):
+        layer(torch.eye(8).repeat(2, 1, 1), torch.randn(1, 8, 4, device=DEV))      # supports on CPU
+    with pytest.raises(AssertionError):
+        layer(torch.eye(8, device=DEV).repeat(3, 1, 1), torch.randn(1, 8, 4, device=DEV))   # K mismatch (GCN.py:31)
+    with pytest.raises(RuntimeError):
+        ops.obs_to_node_major(torch.randn(2, 3, 4, 1))                               # CPU tensor
