@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- region-timesteps/s of the ST-MGCN hot path (fwd + MSE + bwd [+ gradient all-reduce]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl ours|reference]
+
+Contract (driver): prints ONE JSON line on rank 0.  ``value`` = whole-job region-timesteps/s with the inputs
+resident in HBM; ``e2e`` = the same metric through the public module API with HOST (pinned) inputs, the
+host->device copies and a device->host read of the loss inside the timed region; ``roofline`` = the
+Chebyshev SpMM (the forward's 18 recurrence launches at cfg3) timed alone with CUDA events against the
+measured HBM peak; ``cpu_baseline`` = the oracle port (dense supports + nn.LSTM, what the reference executes)
+on this box's host cores on a bounded sample.  ``--impl reference`` times only that CPU path.
+
+Default workload: cfg3 = BASELINE.json configs[2] (4096 regions, 3 graphs, K=3, seq_len=12, batch 64 per
+GPU, fp32) -- the configuration BASELINE.json's metric quotes the SpMM HBM figure on, and the largest fp32
+single-GPU configuration; with N GPUs the per-GPU batch stays 64 (weak scaling; N=8 is cfg4's 512 windows).
+A step's working set (tens of GB of LSTM tape) is far larger than the 126 MB L2, so no explicit L2 flush.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for _p in (REPO, os.path.join(REPO, "st-mgcn_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "region-timesteps/sec (fwd+bwd)"
+UNIT = "region-timesteps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, reasons, sm_max = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                sm_max = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=sm_max, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def spmm_algorithmic_bytes(n, nnz, f_total, k_order, elem=4):
+    """per GCN call K*CSR + N*F*e*(3K-1)."""
+    csr = nnz * 8 + (n + 1) * 4
+    return k_order * csr + n * f_total * elem * (3 * k_order - 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the oracle port (dense supports + nn.LSTM, the reference's algorithm) on host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(w, steps, warmup, sample_batch, log=None):
+    import torch
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import stmgcn_oracle as O
+    from stmgcn_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t0 = time.time()
+    adjs = synth.make_adjacency_list(w)
+    sups = [O.chebyshev_supports_dense(a, w.cheb_order) for a in adjs]      # GCN.py:57-97 (dense, once)
+    prep_s = time.time() - t0
+    params = O.init_params(w.n_graphs, w.seq_len, w.input_dim, w.lstm_hidden, w.lstm_layers, w.gcn_hidden,
+                           w.n_supports, seed=0)
+    x, y = synth.make_inputs(w, seed=0, batch=sample_batch)
+    times = []
+    for i in range(warmup + steps):
+        t1 = time.time()
+        O.dense_loss_and_grads(params, x, y, sups, relu=True, lstm=O.lstm_library)
+        dt = time.time() - t1
+        if i >= warmup:
+            times.append(dt)
+        if log:
+            log(f"[cpu] step {i} {dt:.2f}s")
+    mean = sum(times) / len(times)
+    value = sample_batch * w.n_regions * w.seq_len / mean
+    try:
+        model = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        model = "unknown"
+    return dict(value=value, unit=UNIT, cores=cores, kind="port",
+                sample=f"{w.name} shapes with batch {sample_batch} (of {w.batch}), {steps} timed step(s) after "
+                       f"{warmup} warm-up, fwd+MSE+bwd, dense supports + nn.LSTM as the reference executes; "
+                       f"support preprocessing {prep_s:.1f}s excluded; cpu '{model}'"), mean
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    sample = 4 if total <= 4 else (2 if total <= 12 else 1)
+    cb, mean = cpu_reference_run(w, args.steps, args.warmup, sample)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(w, 1, w.batch), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(w, world, per_gpu_batch):
+    return {"workload": f"{w.name}: {w.n_regions} regions, {w.n_graphs} graphs, Chebyshev K={w.cheb_order}, "
+                        f"seq_len={w.seq_len}, batch={per_gpu_batch}/GPU x {world} GPU(s), fp32, H={w.lstm_hidden} "
+                        f"L={w.lstm_layers} G={w.gcn_hidden} C={w.input_dim}, graph density {w.density}",
+            "global_batch": per_gpu_batch * world, "parallelism": f"dp{world}",
+            "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
+            "step": "forward + MSELoss + backward (+ one gradient all-reduce when world > 1); optimizer excluded"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    from torch import nn
+    import GCN
+    import STMGCN
+    from stmgcn_b200 import _lib, dp, ops, synth
+    from stmgcn_b200.graph import supports_from_dense
+
+    rank, world, local_rank = dp.init_from_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    b = args.batch or w.batch
+
+    # supports: sparse-native construction (no dense N^3 preprocessing); replicated on every rank
+    pre = GCN.Adj_Preprocessor("chebyshev", w.cheb_order)
+    sups = [pre.process_sparse(a).to(dev) for a in synth.make_adjacency_list(w)]
+    torch.manual_seed(0)
+    model = STMGCN.ST_MGCN(**synth.model_kwargs(w)).to(dev)
+    bucket = dp.GradBucket(model)
+    crit = nn.MSELoss(reduction="mean")
+    x_h, y_h = synth.make_inputs(w, seed=100 + rank, batch=b)          # each rank: its own shard of windows
+    x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
+    x_d, y_d = x_h.to(dev), y_h.to(dev)
+
+    def step(x, y):
+        bucket.zero_()
+        out = model(obs_seq=x, sta_adj_list=sups)
+        loss = crit(out, y)
+        loss.backward()
+        bucket.all_reduce_mean_()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident inputs ---------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(x_d, y_d)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms_total = timed(lambda: step(x_d, y_d), args.steps)
+    launches = (_lib.launch_count() - l0) // args.steps
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    units = b * world * w.n_regions * w.seq_len
+    value = units / (ms_step * 1e-3)
+
+    # ---- end to end: host (pinned) inputs through the public module API ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        x_buf, y_buf = torch.empty_like(x_d), torch.empty_like(y_d)
+
+        def e2e_step():
+            x_buf.copy_(x_h, non_blocking=True)
+            y_buf.copy_(y_h, non_blocking=True)
+            loss = step(x_buf, y_buf)
+            return loss.item()                                  # device -> host read of the step's result
+
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps) / args.steps
+        e2e = {"value": units / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": (x_h.numel() + y_h.numel()) * 4, "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e}
+
+    # ---- roofline of the dominant memory-bound kernel: the Chebyshev SpMM (forward's recurrence launches) ----
+    roofline = None
+    if rank == 0:
+        pk, pk_kind = peaks()
+        ssets = [supports_from_dense(s) for s in sups]
+        n, k_ord = w.n_regions, w.cheb_order
+        stacks = [(torch.randn(w.n_supports, n, b, w.seq_len, device=dev),
+                   torch.randn(w.n_supports, n, b, w.lstm_hidden, device=dev)) for _ in ssets]
+
+        def spmm_forward_all():
+            for sset, (st, ss) in zip(ssets, stacks):
+                ops.cheb_stack_(sset, st)
+                ops.cheb_stack_(sset, ss)
+
+        for _ in range(3):
+            spmm_forward_all()
+        reps = 5
+        l1 = _lib.launch_count()
+        ms_spmm = timed(lambda: spmm_forward_all(), reps) / reps if world == 1 else None
+        if ms_spmm is None:      # multi-GPU run: time locally without collectives
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                spmm_forward_all()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_spmm = e0.elapsed_time(e1) / reps
+        n_launch = (_lib.launch_count() - l1) // reps
+        alg = sum(spmm_algorithmic_bytes(n, s.graphs[0].nnz if s.graphs else 0, b * f, k_ord)
+                  for s in ssets for f in (w.seq_len, w.lstm_hidden))
+        achieved = alg / (ms_spmm * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "spmm_row_gather_kernel (Chebyshev recurrence step)",
+                    "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                    "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+                    "algorithmic_bytes_per_forward": alg, "launches_per_forward": n_launch,
+                    "ms_per_forward": ms_spmm, "avg_us_per_launch": ms_spmm * 1e3 / max(n_launch, 1),
+                    "scope": f"all {n_launch} forward recurrence launches of one step ({w.n_graphs} graphs x "
+                             f"(temporal F={b * w.seq_len} + spatial F={b * w.lstm_hidden}) x K={k_ord}), timed alone with "
+                             f"CUDA events; bytes per SURVEY.md 8(d)"}
+        del stacks
+
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _ = cpu_reference_run(w, 1, 1, sample_batch=min(4, b))
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(w, world, b), "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    from stmgcn_b200 import synth
+    w = synth.WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()
