@@ -118,12 +118,18 @@ int32_t stmgcn_gate_bwd(const float* d_s, const float* z, const float* a1, const
  *   hs, cs: (L, T, R, H);  gates: (L, T, R, 4H) post-activation, gate-interleaved (NULL in inference);
  * xo: (R, T, C) node-major observations, s_gate: (B, T) context gate (the modulation xo * s is fused into
  * the layer-0 input read, STMGCN.py:44).  h0/c0: (L, R, H) or NULL (zeros, STMGCN.py:53-57).
+ * wimg: optional per-layer tensor-core weight images (see stmgcn_lstm_pack_tc) or NULL.
  * Step t computes layers 0..L-1.  Limits: H % 4 == 0, H <= 128, C <= 4, L <= 8. */
 int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
                              const float* wx, const float* const* wp, const float* const* bp,
-                             const float* h0, const float* c0, float* hs, float* cs, float* gates,
-                             void* stream);
+                             const float* const* wimg, const float* h0, const float* c0, float* hs, float* cs,
+                             float* gates, void* stream);
+/* Tensor-core operand images of one packed layer (H = 64 only): wp (kd, 4H) -> img, kd/32 k-blocks of
+ * [hi 32 KB | lo 32 KB], each a K-major 128B-swizzled [256][32] fp32 tile of the tf32 hi / lo split
+ * (3xTF32 scheme).  img: kd*256*2 floats.  Passing wimg[l] != NULL to stmgcn_lstm_step_fwd selects the
+ * tcgen05 path for that layer; wimg == NULL (or H != 64) runs the exact-FFMA path. */
+int32_t stmgcn_lstm_pack_tc(const float* wp, int32_t kd, int32_t hid, float* img, void* stream);
 /* BPTT step t (call t = T-1 .. 0).  d_top: (R, H) gradient of hs[L-1][T-1] (read at t = T-1 only).
  * Workspaces, zeroed by the caller before t = T-1: dh_rec, dc: (L, R, H); dx_work: (R, H).
  * gates[l][t] is overwritten IN PLACE with the pre-activation gradients dA (stmgcn_lstm_wgrad reads them).

@@ -11,6 +11,13 @@
 
 using namespace stmgcn;
 
+namespace stmgcn {
+int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, const float* wimg, const float* bias,
+                            const float* wx, const float* xo, const float* sg, int c_in, int t, int t_len,
+                            int64_t b_inner, const float* c_prev, float* h_out, float* c_out, float* gates_out,
+                            int64_t rows, cudaStream_t st);
+}
+
 namespace {
 
 constexpr int kMaxLayers = 8;
@@ -249,8 +256,8 @@ extern "C" {
 int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
                              const float* wx, const float* const* wp, const float* const* bp,
-                             const float* h0, const float* c0, float* hs, float* cs, float* gates,
-                             void* stream) {
+                             const float* const* wimg, const float* h0, const float* c0, float* hs, float* cs,
+                             float* gates, void* stream) {
     STMGCN_REQUIRE(xo && s_gate && wx && wp && bp && hs && cs, STMGCN_ERR_ARG, "lstm_step_fwd: null pointer");
     if (int32_t rc = check_dims("lstm_step_fwd", t, t_len, n_layers, rows, hid, c_in, b_inner)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -288,6 +295,16 @@ int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
         epi.half_units = 256 / 8;
         const int kd = a.nseg * hid;
         int32_t rc;
+        const bool tc_ok = wimg && wimg[l] && hid == 64 && aligned16(epi.h_out) && aligned16(epi.c_out) &&
+                           (!epi.gates_out || aligned16(epi.gates_out)) && (!c_prev || aligned16(c_prev)) &&
+                           (!a.seg[0] || aligned16(a.seg[0])) && (a.nseg < 2 || !a.seg[1] || aligned16(a.seg[1]));
+        if (tc_ok) {   // tcgen05 3xTF32 path (lstm_tc.cu)
+            rc = launch_lstm_cell_tc(a.seg[0], a.nseg > 1 ? a.seg[1] : nullptr, a.nseg, wimg[l], bp[l], epi.wx, xo,
+                                     s_gate, c_in, t, t_len, b_inner, c_prev, epi.h_out, epi.c_out, epi.gates_out,
+                                     rows, st);
+            if (rc) return rc;
+            continue;
+        }
         if (vec_ok(a, wp[l], h4, h4))
             rc = launch_tall<256, true>(a, rows, kd, wp[l], h4, h4, epi, st, "lstm_step_fwd");
         else

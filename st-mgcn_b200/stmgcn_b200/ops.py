@@ -14,6 +14,7 @@ Functions (reference lines they replace):
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -26,6 +27,21 @@ L = _lib.lib
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+_LSTM_PATH = os.environ.get("STMGCN_LSTM_PATH", "tc")
+
+
+def lstm_path() -> str:
+    """"tc": tcgen05 3xTF32 tensor-core kernels where shapes allow (H = 64); "fma": exact-fp32 FFMA kernels."""
+    return _LSTM_PATH
+
+
+def set_lstm_path(path: str) -> None:
+    global _LSTM_PATH
+    if path not in ("tc", "fma"):
+        raise ValueError(path)
+    _LSTM_PATH = path
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -294,10 +310,16 @@ class SharedLSTM(torch.autograd.Function):
         gates = torch.empty((n_layers, t_len, rows, 4 * hid), device=dev, dtype=torch.float32) if need_grad else None
         wp_arr, bp_arr = _lib.ptr_array([w.data_ptr() for w in wp]), _lib.ptr_array([v.data_ptr() for v in bp])
         st = _stream()
+        wimg, wimg_arr = None, None
+        if hid == 64 and lstm_path() == "tc":           # tcgen05 3xTF32 path: pre-swizzled hi/lo weight images
+            wimg = [torch.empty(w.shape[0] * 4 * hid * 2, device=dev, dtype=torch.float32) for w in wp]
+            for w, img in zip(wp, wimg):
+                _lib.check(L.stmgcn_lstm_pack_tc(w.data_ptr(), w.shape[0], hid, img.data_ptr(), st), "lstm_pack_tc")
+            wimg_arr = _lib.ptr_array([v.data_ptr() for v in wimg])
         for t in range(t_len):
             _lib.check(L.stmgcn_lstm_step_fwd(t, t_len, n_layers, rows, hid, c_in, b, xo.data_ptr(),
-                                              s_gate.data_ptr(), wx.data_ptr(), wp_arr, bp_arr, _p(h0c), _p(c0c),
-                                              hs.data_ptr(), cs.data_ptr(), _p(gates), st), "lstm_step_fwd")
+                                              s_gate.data_ptr(), wx.data_ptr(), wp_arr, bp_arr, wimg_arr, _p(h0c),
+                                              _p(c0c), hs.data_ptr(), cs.data_ptr(), _p(gates), st), "lstm_step_fwd")
         ctx.dims = (n, b, t_len, c_in, n_layers, hid)
         if need_grad:
             ctx.save_for_backward(xo, s_gate, h0c, c0c, hs, cs, gates, wx, *wpt)

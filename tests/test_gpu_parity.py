@@ -192,3 +192,32 @@ def test_errors_are_loud():
         layer(torch.eye(8, device=DEV).repeat(3, 1, 1), torch.randn(1, 8, 4, device=DEV))   # K mismatch (GCN.py:31)
     with pytest.raises(RuntimeError):
         ops.obs_to_node_major(torch.randn(2, 3, 4, 1))                               # CPU tensor
+
+
+@pytest.mark.parametrize("rows_n,b,t,c", [(5, 60, 3, 1), (3, 50, 2, 2), (40, 64, 4, 1)])
+def test_lstm_tensor_core_path_matches_exact_fp32_path(rows_n, b, t, c):
+    """tcgen05 3xTF32 LSTM forward vs the exact-FFMA kernels on the same inputs (ragged 128-row tiles)."""
+    from stmgcn_b200 import ops
+    hid, lyr = 64, 3
+    gen = torch.Generator().manual_seed(rows_n * 100 + t)
+    xo = torch.randn(rows_n, b, t, c, generator=gen).to(DEV)
+    s = torch.rand(b, t, generator=gen).to(DEV)
+    ws = []
+    for l in range(lyr):
+        in_l = c if l == 0 else hid
+        ws += [torch.randn(4 * hid, in_l, generator=gen) * 0.2, torch.randn(4 * hid, hid, generator=gen) * 0.2,
+               torch.randn(4 * hid, generator=gen) * 0.1, torch.randn(4 * hid, generator=gen) * 0.1]
+    ws = [w.to(DEV) for w in ws]
+    h0 = (torch.randn(lyr, rows_n * b, hid, generator=gen) * 0.3).to(DEV)
+    c0 = (torch.randn(lyr, rows_n * b, hid, generator=gen) * 0.3).to(DEV)
+    outs = {}
+    old = ops.lstm_path()
+    try:
+        for path in ("fma", "tc"):
+            ops.set_lstm_path(path)
+            with torch.no_grad():
+                outs[path] = [v.clone() for v in ops.SharedLSTM.apply(xo, s, h0, c0, lyr, hid, *ws)]
+    finally:
+        ops.set_lstm_path(old)
+    for name, a, b_ in zip(("h_top", "h_n", "c_n"), outs["tc"], outs["fma"]):
+        assert_close(a.cpu().numpy(), b_.cpu().numpy(), f"tc vs fma {name}", 2e-5)
