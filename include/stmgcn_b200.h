@@ -125,21 +125,25 @@ int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
                              const float* wx, const float* const* wp, const float* const* bp,
                              const float* const* wimg, const float* h0, const float* c0, float* hs, float* cs,
                              float* gates, void* stream);
-/* Tensor-core operand images of one packed layer (H = 64 only): wp (kd, 4H) -> img, kd/32 k-blocks of
- * [hi 32 KB | lo 32 KB], each a K-major 128B-swizzled [256][32] fp32 tile of the tf32 hi / lo split
- * (3xTF32 scheme).  img: kd*256*2 floats.  Passing wimg[l] != NULL to stmgcn_lstm_step_fwd selects the
- * tcgen05 path for that layer; wimg == NULL (or H != 64) runs the exact-FFMA path. */
-int32_t stmgcn_lstm_pack_tc(const float* wp, int32_t kd, int32_t hid, float* img, void* stream);
+/* Tensor-core operand images of one packed layer (H = 64 only).  wp (kd, 4H) -> two images, each kd*256*2
+ * floats, made of 32-wide k-blocks of [hi | lo] K-major 128B-swizzled fp32 tiles holding the tf32 hi / lo split
+ * of the weights (3xTF32 scheme): img_fwd = operand of gates = A . Wp (tiles [256][32]); img_bwd (may be NULL) =
+ * operand of [dx | dh] = dA . Wp^T (tiles [kd][32]).  Passing wimg[l] / wimg_t[l] != NULL to
+ * stmgcn_lstm_step_fwd / _bwd selects the tcgen05 kernels for that layer; NULL (or H != 64) runs the exact-FFMA
+ * kernels.  Both paths read and write the same tape. */
+int32_t stmgcn_lstm_pack_tc(const float* wp, int32_t kd, int32_t hid, float* img_fwd, float* img_bwd,
+                            void* stream);
 /* BPTT step t (call t = T-1 .. 0).  d_top: (R, H) gradient of hs[L-1][T-1] (read at t = T-1 only).
  * Workspaces, zeroed by the caller before t = T-1: dh_rec, dc: (L, R, H); dx_work: (R, H).
  * gates[l][t] is overwritten IN PLACE with the pre-activation gradients dA (stmgcn_lstm_wgrad reads them).
+ * wimg_t: optional per-layer tensor-core images of Wp^T (stmgcn_lstm_pack_tc) or NULL.
  * Accumulates (+=; caller zeroes): d_s (B,T) = sum_{n,c} dxmod * xo (gate adjoint, STMGCN.py:44),
  * dwx (C,4H), dbp[l] (4H). */
 int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
-                             const float* wx, const float* const* wpt, const float* c0, const float* cs,
-                             float* gates, const float* d_top, float* dh_rec, float* dc, float* dx_work,
-                             float* d_s, float* dwx, float* const* dbp, void* stream);
+                             const float* wx, const float* const* wpt, const float* const* wimg_t,
+                             const float* c0, const float* cs, float* gates, const float* d_top, float* dh_rec,
+                             float* dc, float* dx_work, float* d_s, float* dwx, float* const* dbp, void* stream);
 /* weight gradients of one layer after all stmgcn_lstm_step_bwd calls:
  * dwp (kd_l, 4H) += [h_below_t | h_{t-1}]^T dA summed over all (t, r). */
 int32_t stmgcn_lstm_wgrad(int32_t layer, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,

@@ -16,6 +16,11 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, cons
                             const float* wx, const float* xo, const float* sg, int c_in, int t, int t_len,
                             int64_t b_inner, const float* c_prev, float* h_out, float* c_out, float* gates_out,
                             int64_t rows, cudaStream_t st);
+int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* c_prev, const float* dh_in,
+                           float* dh_rec, float* dc, float* dx_out, const float* wimg_t, float* dbp, const float* wx,
+                           float* dwx, const float* xo, const float* sg, float* d_s, int c_in, int t, int t_len,
+                           int64_t b_inner, int64_t rows, cudaStream_t st);
+int lstm_tc_max_c_bwd();
 }
 
 namespace {
@@ -316,9 +321,9 @@ int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
 
 int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
-                             const float* wx, const float* const* wpt, const float* c0, const float* cs,
-                             float* gates, const float* d_top, float* dh_rec, float* dc, float* dx_work,
-                             float* d_s, float* dwx, float* const* dbp, void* stream) {
+                             const float* wx, const float* const* wpt, const float* const* wimg_t,
+                             const float* c0, const float* cs, float* gates, const float* d_top, float* dh_rec,
+                             float* dc, float* dx_work, float* d_s, float* dwx, float* const* dbp, void* stream) {
     STMGCN_REQUIRE(xo && s_gate && wx && wpt && cs && gates && dh_rec && dc && dx_work && d_s && dwx && dbp,
                    STMGCN_ERR_ARG, "lstm_step_bwd: null pointer");
     if (int32_t rc = check_dims("lstm_step_bwd", t, t_len, n_layers, rows, hid, c_in, b_inner)) return rc;
@@ -333,6 +338,15 @@ int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
         const float* c_prev = t > 0 ? cs + ((int64_t)(l * t_len + t - 1)) * rh : (c0 ? c0 + (int64_t)l * rh : nullptr);
         const float* dh_in = (l == n_layers - 1) ? ((t == t_len - 1) ? d_top : nullptr) : dx_work;
         const bool l0 = (l == 0);
+        if (wimg_t && wimg_t[l] && hid == 64 && (!l0 || c_in <= lstm_tc_max_c_bwd()) && aligned16(g_lt)) {
+            // tcgen05 path: pointwise + data GEMM fused in one kernel (lstm_tc.cu)
+            int32_t rc = launch_lstm_bwd_tc(l0 ? 64 : 128, g_lt, c_t, c_prev, dh_in, dh_rec + (int64_t)l * rh,
+                                            dc + (int64_t)l * rh, l0 ? nullptr : dx_work, wimg_t[l], dbp[l],
+                                            l0 ? wx : nullptr, l0 ? dwx : nullptr, xo, s_gate, d_s, c_in, t, t_len,
+                                            b_inner, rows, st);
+            if (rc) return rc;
+            continue;
+        }
         size_t smem = (size_t)h4 * (1 + (l0 ? c_in : 0)) * sizeof(float);
         if (l0 && b_inner <= 2048) smem += (size_t)b_inner * sizeof(float);
         lstm_bwd_pointwise_kernel<<<grid_pw, 256, smem, st>>>(

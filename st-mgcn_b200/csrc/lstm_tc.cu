@@ -1,18 +1,20 @@
-// K3b on the 5th-gen tensor cores: one LSTM layer-step for a 128-row tile as
-//     gates[128 x 256] = [h_below | h_prev][128 x Kd] . Wp[Kd x 256]        (reference: nn.LSTM, STMGCN.py:48)
-// with tcgen05.mma kind::tf32 in the 3xTF32 scheme (tc_common.cuh), fp32 accumulators in TMEM, and the cell
-// nonlinearity + state update fused into the TMEM->register epilogue.  H = 64 only (the reference's value,
-// Main.py:62); other sizes take the exact-FFMA path in lstm.cu.
+// K3b on the 5th-gen tensor cores (tcgen05, TMEM accumulators, 3xTF32 -- see tc_common.cuh), H = 64 only
+// (the reference's value, Main.py:62); other sizes take the exact-FFMA kernels in lstm.cu.
 //
-// CTA = 9 warps, persistent over row tiles, 1 CTA / SM (192 KB of operand stages, all 512 TMEM columns):
-//   warps 0-3  epilogue : tcgen05.ld its TMEM lane quadrant, bias + layer-0 input term, sigmoid/tanh, c/h update,
-//                         stores h, c (and the gate tape for the backward)
-//   warps 4-7  loaders  : read the A rows from HBM (coalesced 128-bit), split into tf32 hi/lo and write both
-//                         K-major 128B-swizzled operand tiles; one thread also starts the bulk copies (TMA unit)
-//                         of the pre-swizzled hi/lo weight images for the same k-block
-//   warp  8    MMA      : single-thread tcgen05.mma issue, 12 MMAs (3 passes x 4 k-slices) per 32-wide k-block;
-//                         tcgen05.commit releases operand stages and publishes accumulators
-// Pipelines: 2 operand stages (full/empty mbarriers), 2 TMEM accumulators (tmem_full/tmem_empty).
+//  forward  (one launch per layer-step):  gates[128 x 256] = [h_below | h_prev][128 x Kd] . Wp[Kd x 256]
+//           + fused LSTM cell epilogue (reference: nn.LSTM inside CG_LSTM, STMGCN.py:48).
+//  backward (one launch per layer-step):  the loader warps turn the saved gates into the pre-activation
+//           gradients dA (BPTT pointwise math), write dA back over the tape (consumed by stmgcn_lstm_wgrad) and
+//           straight into the swizzled operand tiles of  [dx_below | dh_prev][128 x Kd] = dA[128 x 256] . Wp^T.
+//
+// CTA anatomy (persistent over 128-row tiles, 1 CTA / SM):
+//   epilogue warps : tcgen05.ld their TMEM lane quadrant -> registers -> math -> global
+//   loader warps   : HBM -> registers -> tf32 hi/lo split -> K-major 128B-swizzled smem operand tiles;
+//                    one thread also starts the bulk copies (TMA unit, UBLKCP) of the pre-swizzled hi/lo weight
+//                    images for the same k-block
+//   MMA warp       : one thread issues tcgen05.mma kind::tf32, 12 per 32-wide k-block (3 passes x 4 k-slices);
+//                    tcgen05.commit releases operand stages / publishes accumulators
+// Pipelines: operand stages (full/empty mbarriers) and two TMEM accumulators (tmem_full/tmem_empty).
 #include "tc_common.cuh"
 
 using namespace stmgcn;
@@ -21,29 +23,102 @@ using namespace stmgcn::tc;
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kTileN = 256;          // 4H, H = 64
 constexpr int kKB = 32;              // k-block: one 128-byte swizzle row of fp32
 constexpr int kHid = 64;
-constexpr int kMaxC = 4;
-constexpr int kStages = 2;
+constexpr int kGateCols = 256;       // 4H
+constexpr int kMaxStages = 3;
 constexpr int kAccs = 2;
-constexpr int kABytes = kTileM * kKB * 4;            // 16 KB per hi or lo tile
-constexpr int kBBytes = kTileN * kKB * 4;            // 32 KB per hi or lo tile
-constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // 96 KB
-constexpr int kThreads = 288;
+constexpr int kABytes = kTileM * kKB * 4;            // 16 KB per hi or lo A tile
 constexpr int kNumLoaders = 128;
-constexpr int kNumEpi = 128;
 
-struct SmemTail {
-    float bias[kTileN];
-    float wx[kMaxC * kTileN];
-    uint64_t full[kStages];
-    uint64_t empty[kStages];
+struct Barriers {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
     uint64_t tmem_full[kAccs];
     uint64_t tmem_empty[kAccs];
     uint32_t tmem_base;
 };
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + sizeof(SmemTail);
+
+__device__ __forceinline__ void init_barriers(Barriers* b, int stages, int n_epi_threads) {
+    for (int s = 0; s < stages; ++s) {
+        mbar_init(&b->full[s], kNumLoaders + 1);
+        mbar_init(&b->empty[s], 1);
+    }
+    for (int a = 0; a < kAccs; ++a) {
+        mbar_init(&b->tmem_full[a], 1);
+        mbar_init(&b->tmem_empty[a], n_epi_threads);
+    }
+    fence_barrier_init();
+}
+
+// The MMA warp: for every tile, for every k-block: wait operands, issue 3 x 4 MMAs, release the stage.
+template <int N, int STAGES>
+__device__ __forceinline__ void mma_issuer(Barriers* bar, uint8_t* smem, int stage_bytes, int b_bytes, int nkb,
+                                           int n_tiles, uint32_t tmem_base, int lane) {
+    constexpr uint32_t idesc = idesc_tf32(kTileM, N);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const int a = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        mbar_wait(&bar->tmem_empty[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)a * N;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&bar->full[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t a_hi = smem_desc_k_sw128(st);
+                const uint64_t a_lo = smem_desc_k_sw128(st + kABytes);
+                const uint64_t b_hi = smem_desc_k_sw128(st + 2 * kABytes);
+                const uint64_t b_lo = smem_desc_k_sw128(st + 2 * kABytes + b_bytes);
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint64_t da = (pass == 1) ? a_lo : a_hi;
+                    const uint64_t db = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+                    for (int k = 0; k < kKB / 8; ++k) {
+                        const uint32_t acc = (kb > 0 || pass > 0 || k > 0) ? 1u : 0u;
+                        mma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
+                    }
+                }
+                mma_commit(&bar->empty[s]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) mma_commit(&bar->tmem_full[a]);
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void split_store(uint8_t* st, uint32_t off, const float4& v) {
+    float4 hi, lo;
+    hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+    lo.x = tf32_lo(v.x, hi.x); lo.y = tf32_lo(v.y, hi.y); lo.z = tf32_lo(v.z, hi.z); lo.w = tf32_lo(v.w, hi.w);
+    *reinterpret_cast<float4*>(st + off) = hi;
+    *reinterpret_cast<float4*>(st + kABytes + off) = lo;
+}
+
+// =====================================================================================================
+// forward cell
+// =====================================================================================================
+constexpr int kFwdN = kGateCols;
+constexpr int kFwdStages = 2;
+constexpr int kFwdBBytes = kFwdN * kKB * 4;                       // 32 KB
+constexpr int kFwdStageBytes = 2 * kABytes + 2 * kFwdBBytes;      // 96 KB
+constexpr int kFwdEpiWarps = 8;
+constexpr int kFwdThreads = (kFwdEpiWarps + 4 + 1) * 32;          // 416
+constexpr int kStagingBytes = 32 * 32 * 4;                        // per epilogue warp: [32 rows][32 cols] fp32
+constexpr int kMaxC = 4;
+
+struct FwdTail {
+    float bias[kGateCols];
+    Barriers bar;
+};
+constexpr size_t kFwdSmem = 1024 + (size_t)kFwdStages * kFwdStageBytes + (size_t)kFwdEpiWarps * kStagingBytes +
+                            sizeof(FwdTail);
 
 struct CellParams {
     const float* seg0;       // (rows, 64) first K segment  (h_below for l>0, h_prev for l==0) or nullptr = zeros
@@ -64,118 +139,75 @@ struct CellParams {
     int n_tiles;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) lstm_cell_tc_kernel(const __grid_constant__ CellParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __grid_constant__ CellParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    SmemTail* tail = (SmemTail*)(smem + (size_t)kStages * kStageBytes);
+    uint8_t* staging = smem + (size_t)kFwdStages * kFwdStageBytes;
+    FwdTail* tail = (FwdTail*)(staging + (size_t)kFwdEpiWarps * kStagingBytes);
+    Barriers* bar = &tail->bar;
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
+    constexpr int kMmaWarp = kFwdEpiWarps + 4;
 
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&tail->full[s], kNumLoaders + 1);
-            mbar_init(&tail->empty[s], 1);
-        }
-        for (int a = 0; a < kAccs; ++a) {
-            mbar_init(&tail->tmem_full[a], 1);
-            mbar_init(&tail->tmem_empty[a], kNumEpi);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 8) tmem_alloc(&tail->tmem_base, 512);
-    for (int i = tid; i < kTileN; i += kThreads) tail->bias[i] = p.bias[i];
-    if (p.wx != nullptr)
-        for (int i = tid; i < p.c_in * kTileN; i += kThreads) tail->wx[i] = p.wx[i];
+    if (tid == 0) init_barriers(bar, kFwdStages, kFwdEpiWarps * 32);
+    if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, 512);
+    for (int i = tid; i < kGateCols; i += kFwdThreads) tail->bias[i] = p.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tail->tmem_base;
+    const uint32_t tmem_base = bar->tmem_base;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= kFwdEpiWarps && warp < kMmaWarp) {
         // ===================== loaders / tf32 splitters =====================
-        const int ltid = tid - 128;
+        const int ltid = tid - kFwdEpiWarps * 32;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int64_t row_base = (int64_t)tile * kTileM;
             for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&tail->empty[s], ph ^ 1);
-                uint8_t* st = smem + (size_t)s * kStageBytes;
-                if (ltid == 0) {
-                    mbar_arrive_expect_tx(&tail->full[s], 2 * kBBytes);
-                    const float* src = p.wimg + (size_t)kb * (2 * kBBytes / 4);
-                    bulk_g2s(st + 2 * kABytes, src, kBBytes, &tail->full[s]);
-                    bulk_g2s(st + 2 * kABytes + kBBytes, src + kBBytes / 4, kBBytes, &tail->full[s]);
-                }
+                const int s = it % kFwdStages;
+                const uint32_t ph = (it / kFwdStages) & 1;
                 const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
                 const int koff = (kb & 1) * kKB;
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {            // issue the HBM reads before waiting for the slot
+                    const int idx = ltid + i * kNumLoaders;
+                    const int64_t r = row_base + (idx >> 3);
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (seg != nullptr && r < p.rows)
+                        v[i] = *reinterpret_cast<const float4*>(seg + r * kHid + koff + (idx & 7) * 4);
+                }
+                mbar_wait(&bar->empty[s], ph ^ 1);
+                uint8_t* st = smem + (size_t)s * kFwdStageBytes;
+                if (ltid == 0) {
+                    mbar_arrive_expect_tx(&bar->full[s], 2 * kFwdBBytes);
+                    const float* src = p.wimg + (size_t)kb * (2 * kFwdBBytes / 4);
+                    bulk_g2s(st + 2 * kABytes, src, kFwdBBytes, &bar->full[s]);
+                    bulk_g2s(st + 2 * kABytes + kFwdBBytes, src + kFwdBBytes / 4, kFwdBBytes, &bar->full[s]);
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int idx = ltid + i * kNumLoaders;
                     const int row = idx >> 3, c = idx & 7;
-                    const int64_t r = row_base + row;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (seg != nullptr && r < p.rows)
-                        v = *reinterpret_cast<const float4*>(seg + r * kHid + koff + c * 4);
-                    float4 hi, lo;
-                    hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
-                    lo.x = tf32_lo(v.x, hi.x); lo.y = tf32_lo(v.y, hi.y); lo.z = tf32_lo(v.z, hi.z); lo.w = tf32_lo(v.w, hi.w);
-                    const uint32_t off = (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4);
-                    *reinterpret_cast<float4*>(st + off) = hi;
-                    *reinterpret_cast<float4*>(st + kABytes + off) = lo;
+                    split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), v[i]);
                 }
                 fence_proxy_async_smem();
-                mbar_arrive(&tail->full[s]);
+                mbar_arrive(&bar->full[s]);
             }
         }
-    } else if (warp == 8) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = idesc_tf32(kTileM, kTileN);
-        uint32_t it = 0, tcount = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
-            const int a = tcount & 1;
-            const uint32_t aph = (tcount >> 1) & 1;
-            mbar_wait(&tail->tmem_empty[a], aph ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)a * kTileN;
-            for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&tail->full[s], ph);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t st = smem_u32(smem + (size_t)s * kStageBytes);
-                    const uint64_t a_hi = smem_desc_k_sw128(st);
-                    const uint64_t a_lo = smem_desc_k_sw128(st + kABytes);
-                    const uint64_t b_hi = smem_desc_k_sw128(st + 2 * kABytes);
-                    const uint64_t b_lo = smem_desc_k_sw128(st + 2 * kABytes + kBBytes);
-#pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint64_t da = (pass == 1) ? a_lo : a_hi;
-                        const uint64_t db = (pass == 2) ? b_lo : b_hi;
-#pragma unroll
-                        for (int k = 0; k < kKB / 8; ++k) {
-                            const uint32_t acc = (kb > 0 || pass > 0 || k > 0) ? 1u : 0u;
-                            mma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
-                        }
-                    }
-                    mma_commit(&tail->empty[s]);
-                }
-                __syncwarp();
-            }
-            if (lane == 0) mma_commit(&tail->tmem_full[a]);
-            __syncwarp();
-        }
+    } else if (warp == kMmaWarp) {
+        mma_issuer<kFwdN, kFwdStages>(bar, smem, kFwdStageBytes, kFwdBBytes, p.nkb, p.n_tiles, tmem_base, lane);
     } else {
-        // ===================== epilogue: LSTM cell =====================
-        const int etid = tid;            // 0..127 == TMEM lane == row in tile
+        // ===================== epilogue: LSTM cell (8 warps: TMEM lane quadrant q, column half hsel) ============
+        const int q = warp & 3, hsel = warp >> 2;
+        float* stg = reinterpret_cast<float*>(staging + (size_t)warp * kStagingBytes);
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
             const int a = tcount & 1;
             const uint32_t aph = (tcount >> 1) & 1;
-            const int64_t r = (int64_t)tile * kTileM + etid;
+            const int64_t r0 = (int64_t)tile * kTileM + q * 32;     // first row of this warp
+            const int64_t r = r0 + lane;
             const bool valid = r < p.rows;
             float xs[kMaxC];
 #pragma unroll
@@ -186,50 +218,54 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_cell_tc_kernel(const __grid_
                 for (int c = 0; c < kMaxC; ++c)
                     if (c < p.c_in) xs[c] = p.xo[(r * p.t_len + p.t) * p.c_in + c] * sv;
             }
-            mbar_wait(&tail->tmem_full[a], aph);
+            float4 cpa = make_float4(0.f, 0.f, 0.f, 0.f), cpb = cpa;
+            if (p.c_prev != nullptr && valid) {
+                cpa = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + hsel * 32);
+                cpb = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + hsel * 32 + 4);
+            }
+            mbar_wait(&bar->tmem_full[a], aph);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * kTileN;
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * kFwdN;
 #pragma unroll 1
-            for (int chunk = 0; chunk < kTileN / 32; ++chunk) {
+            for (int ci = 0; ci < 4; ++ci) {
+                const int chunk = hsel * 4 + ci;                 // 32 gate columns = units [8*chunk, 8*chunk+8)
                 uint32_t v[32];
                 tmem_ld32(t_row + chunk * 32, v);
+                const float cp[8] = {cpa.x, cpa.y, cpa.z, cpa.w, cpb.x, cpb.y, cpb.z, cpb.w};
+                if (ci < 3 && p.c_prev != nullptr && valid) {    // prefetch the next chunk's cell state
+                    cpa = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + (chunk + 1) * 8);
+                    cpb = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + (chunk + 1) * 8 + 4);
+                }
                 tmem_ld_wait();
-                if (valid) {
-                    float cp[8];
-                    if (p.c_prev != nullptr) {
-                        const float4 c0 = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + chunk * 8);
-                        const float4 c1 = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + chunk * 8 + 4);
-                        cp[0] = c0.x; cp[1] = c0.y; cp[2] = c0.z; cp[3] = c0.w;
-                        cp[4] = c1.x; cp[5] = c1.y; cp[6] = c1.z; cp[7] = c1.w;
-                    } else {
+                float hn[8], cn[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) cp[u] = 0.f;
-                    }
-                    float hn[8], cn[8];
+                for (int u = 0; u < 8; ++u) {
+                    const int col = chunk * 32 + 4 * u;
+                    float pi = __uint_as_float(v[4 * u + 0]) + tail->bias[col + 0];
+                    float pf = __uint_as_float(v[4 * u + 1]) + tail->bias[col + 1];
+                    float pg = __uint_as_float(v[4 * u + 2]) + tail->bias[col + 2];
+                    float po = __uint_as_float(v[4 * u + 3]) + tail->bias[col + 3];
+                    if (p.wx != nullptr) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int col = chunk * 32 + 4 * u;
-                        float pi = __uint_as_float(v[4 * u + 0]) + tail->bias[col + 0];
-                        float pf = __uint_as_float(v[4 * u + 1]) + tail->bias[col + 1];
-                        float pg = __uint_as_float(v[4 * u + 2]) + tail->bias[col + 2];
-                        float po = __uint_as_float(v[4 * u + 3]) + tail->bias[col + 3];
-                        if (p.wx != nullptr) {
-#pragma unroll
-                            for (int c = 0; c < kMaxC; ++c) {
-                                if (c < p.c_in) {
-                                    pi = fmaf(xs[c], tail->wx[c * kTileN + col + 0], pi);
-                                    pf = fmaf(xs[c], tail->wx[c * kTileN + col + 1], pf);
-                                    pg = fmaf(xs[c], tail->wx[c * kTileN + col + 2], pg);
-                                    po = fmaf(xs[c], tail->wx[c * kTileN + col + 3], po);
-                                }
+                        for (int c = 0; c < kMaxC; ++c) {
+                            if (c < p.c_in) {
+                                const float4 wv = __ldg(reinterpret_cast<const float4*>(p.wx + c * kGateCols + col));
+                                pi = fmaf(xs[c], wv.x, pi);
+                                pf = fmaf(xs[c], wv.y, pf);
+                                pg = fmaf(xs[c], wv.z, pg);
+                                po = fmaf(xs[c], wv.w, po);
                             }
                         }
-                        const float gi = sigmoidf_(pi), gf = sigmoidf_(pf), gg = tanhf_(pg), go = sigmoidf_(po);
-                        cn[u] = fmaf(gf, cp[u], gi * gg);
-                        hn[u] = go * tanhf_(cn[u]);
-                        if (p.gates_out != nullptr)
-                            *reinterpret_cast<float4*>(p.gates_out + r * kTileN + col) = make_float4(gi, gf, gg, go);
                     }
+                    const float gi = sigmoidf_(pi), gf = sigmoidf_(pf), gg = tanhf_(pg), go = sigmoidf_(po);
+                    cn[u] = fmaf(gf, cp[u], gi * gg);
+                    hn[u] = go * tanhf_(cn[u]);
+                    v[4 * u + 0] = __float_as_uint(gi);
+                    v[4 * u + 1] = __float_as_uint(gf);
+                    v[4 * u + 2] = __float_as_uint(gg);
+                    v[4 * u + 3] = __float_as_uint(go);
+                }
+                if (valid) {
                     float* hd = p.h_out + r * kHid + chunk * 8;
                     float* cd = p.c_out + r * kHid + chunk * 8;
                     *reinterpret_cast<float4*>(hd) = make_float4(hn[0], hn[1], hn[2], hn[3]);
@@ -237,30 +273,290 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_cell_tc_kernel(const __grid_
                     *reinterpret_cast<float4*>(cd) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                     *reinterpret_cast<float4*>(cd + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
                 }
+                if (p.gates_out != nullptr) {
+                    // gate tape: transpose through this warp's staging tile so every store instruction writes
+                    // 4 full 128-byte row segments instead of 32 scattered 16-byte pieces
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        *reinterpret_cast<uint4*>(stg + lane * 32 + ((u ^ (lane & 7)) << 2)) =
+                            make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + (lane >> 3), qq = lane & 7;
+                        const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 32 + ((qq ^ (row & 7)) << 2));
+                        if (r0 + row < p.rows)
+                            *reinterpret_cast<uint4*>(p.gates_out + (r0 + row) * kGateCols + chunk * 32 + qq * 4) = val;
+                    }
+                }
             }
             tc_fence_before();
-            mbar_arrive(&tail->tmem_empty[a]);
+            mbar_arrive(&bar->tmem_empty[a]);
         }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 8) tmem_dealloc(tmem_base, 512);
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
-// wp (kd, 256) [k][n] -> per k-block: hi image [256][32] then lo image, both K-major with the 128-byte swizzle
-__global__ void pack_weights_tc_kernel(const float* __restrict__ wp, int kd, float* __restrict__ img) {
-    const int total = kd * kTileN;
+// =====================================================================================================
+// backward: pointwise dA in the loader + data GEMM  [dx_below | dh_prev] = dA . Wp^T
+// =====================================================================================================
+constexpr int kBwdStages = 3;
+constexpr int kBwdEpiWarps = 4;
+constexpr int kBwdThreads = (kBwdEpiWarps + 4 + 1) * 32;          // 288
+constexpr int kBwdNkb = kGateCols / kKB;                          // 8
+constexpr int kBwdMaxC = 1;                                       // layer-0 TC backward handles input_dim 1
+
+struct BwdTail {
+    float s_db[kGateCols];
+    float s_dwx[kBwdMaxC * kGateCols];
+    float s_ds[2048];
+    Barriers bar;
+};
+template <int N>
+struct BwdCfg {
+    static constexpr int kBBytes = N * kKB * 4;
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    static constexpr size_t kSmem = 1024 + (size_t)kBwdStages * kStageBytes + sizeof(BwdTail);
+    static constexpr int kTmemCols = 2 * N;      // 256 or 128 (power of two >= 32)
+};
+
+struct BwdParams {
+    float* gates;            // (rows,256) in: post-activation i,f,g,o (interleaved); out: dA
+    const float* c_t;        // (rows,64)
+    const float* c_prev;     // (rows,64) or nullptr
+    const float* dh_in;      // (rows,64) or nullptr   gradient from the layer above (or d_top)
+    float* dh_rec;           // (rows,64) in: recurrent gradient for this step; out: for step t-1
+    float* dc;               // (rows,64) in/out
+    float* dx_out;           // (rows,64) or nullptr (layer 0): gradient for the layer below
+    const float* wimg_t;     // 8 k-blocks x [hi | lo] images of Wp^T, [N][32] each
+    float* dbp;              // (256) +=
+    const float* wx;         // layer 0: (C,256), else nullptr
+    float* dwx;              // (C,256) +=
+    const float* xo;
+    const float* sg;
+    float* d_s;              // (B,T) +=
+    int c_in, t, t_len;
+    int64_t b_inner;
+    int64_t rows;
+    int n_tiles;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __grid_constant__ BwdParams p) {
+    using Cfg = BwdCfg<N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    BwdTail* tail = (BwdTail*)(smem + (size_t)kBwdStages * Cfg::kStageBytes);
+    Barriers* bar = &tail->bar;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    constexpr int kMmaWarp = kBwdEpiWarps + 4;
+    constexpr bool l0 = (N == 64);               // layer 0 <=> kd = 64 (no layer below; carries the gate adjoint)
+    const bool ds_smem = l0 && p.b_inner <= 2048;
+
+    if (tid == 0) init_barriers(bar, kBwdStages, kBwdEpiWarps * 32);
+    if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, Cfg::kTmemCols);
+    for (int i = tid; i < kGateCols; i += kBwdThreads) tail->s_db[i] = 0.f;
+    for (int i = tid; i < kBwdMaxC * kGateCols; i += kBwdThreads) tail->s_dwx[i] = 0.f;
+    if (ds_smem)
+        for (int i = tid; i < (int)p.b_inner; i += kBwdThreads) tail->s_ds[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bar->tmem_base;
+
+    if (warp >= kBwdEpiWarps && warp < kMmaWarp) {
+        // ===================== loaders: BPTT pointwise -> dA -> operand tiles =====================
+        const int ltid = tid - kBwdEpiWarps * 32;
+        const int c = ltid & 7;                  // unit within the k-block (fixed per thread)
+        const int rsub = ltid >> 3;              // rows rsub + 16*i
+        float4 acc_b[kBwdNkb];
+        float4 acc_x[kBwdMaxC][kBwdNkb];
+#pragma unroll
+        for (int kb = 0; kb < kBwdNkb; ++kb) {
+            acc_b[kb] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int ch = 0; ch < kBwdMaxC; ++ch) acc_x[ch][kb] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int64_t row_base = (int64_t)tile * kTileM;
+            float xs[8][kBwdMaxC];
+            float dxs[8][kBwdMaxC];
+            if (l0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int64_t r = row_base + rsub + 16 * i;
+                    const float sv = (r < p.rows) ? p.sg[(r % p.b_inner) * p.t_len + p.t] : 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < kBwdMaxC; ++ch) {
+                        xs[i][ch] = (ch < p.c_in && r < p.rows) ? p.xo[(r * p.t_len + p.t) * p.c_in + ch] * sv : 0.f;
+                        dxs[i][ch] = 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int kb = 0; kb < kBwdNkb; ++kb, ++it) {
+                const int s = it % kBwdStages;
+                const uint32_t ph = (it / kBwdStages) & 1;
+                const int unit = kb * 8 + c;
+                float4 da[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int64_t r = row_base + rsub + 16 * i;
+                    da[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < p.rows) {
+                        const int64_t e = r * kHid + unit;
+                        const float4 g = *reinterpret_cast<const float4*>(p.gates + r * kGateCols + 4 * unit);
+                        float dh = p.dh_rec[e];
+                        if (p.dh_in) dh += p.dh_in[e];
+                        const float tc_ = tanhf_(p.c_t[e]);
+                        const float cpv = p.c_prev ? p.c_prev[e] : 0.f;
+                        const float dcv = p.dc[e] + dh * g.w * (1.f - tc_ * tc_);
+                        da[i].x = dcv * g.z * g.x * (1.f - g.x);
+                        da[i].y = dcv * cpv * g.y * (1.f - g.y);
+                        da[i].z = dcv * g.x * (1.f - g.z * g.z);
+                        da[i].w = dh * tc_ * g.w * (1.f - g.w);
+                        p.dc[e] = dcv * g.y;
+                        *reinterpret_cast<float4*>(p.gates + r * kGateCols + 4 * unit) = da[i];
+                        acc_b[kb].x += da[i].x; acc_b[kb].y += da[i].y; acc_b[kb].z += da[i].z; acc_b[kb].w += da[i].w;
+                        if (l0) {
+#pragma unroll
+                            for (int ch = 0; ch < kBwdMaxC; ++ch) {
+                                if (ch < p.c_in) {
+                                    acc_x[ch][kb].x = fmaf(xs[i][ch], da[i].x, acc_x[ch][kb].x);
+                                    acc_x[ch][kb].y = fmaf(xs[i][ch], da[i].y, acc_x[ch][kb].y);
+                                    acc_x[ch][kb].z = fmaf(xs[i][ch], da[i].z, acc_x[ch][kb].z);
+                                    acc_x[ch][kb].w = fmaf(xs[i][ch], da[i].w, acc_x[ch][kb].w);
+                                    const float4 wv = __ldg(reinterpret_cast<const float4*>(p.wx + ch * kGateCols + 4 * unit));
+                                    dxs[i][ch] += da[i].x * wv.x + da[i].y * wv.y + da[i].z * wv.z + da[i].w * wv.w;
+                                }
+                            }
+                        }
+                    }
+                }
+                mbar_wait(&bar->empty[s], ph ^ 1);
+                uint8_t* st = smem + (size_t)s * Cfg::kStageBytes;
+                if (ltid == 0) {
+                    mbar_arrive_expect_tx(&bar->full[s], 2 * Cfg::kBBytes);
+                    const float* src = p.wimg_t + (size_t)kb * (2 * Cfg::kBBytes / 4);
+                    bulk_g2s(st + 2 * kABytes, src, Cfg::kBBytes, &bar->full[s]);
+                    bulk_g2s(st + 2 * kABytes + Cfg::kBBytes, src + Cfg::kBBytes / 4, Cfg::kBBytes, &bar->full[s]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = rsub + 16 * i;
+                    split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), da[i]);
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&bar->full[s]);
+            }
+            if (l0) {     // gate adjoint: d s[b,t] += sum_c dxmod[r,c] * xo[r,t,c]  (STMGCN.py:44)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int64_t r = row_base + rsub + 16 * i;
+                    float contrib = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < kBwdMaxC; ++ch) {
+                        float d = dxs[i][ch];
+                        d += __shfl_xor_sync(0xffffffffu, d, 1);
+                        d += __shfl_xor_sync(0xffffffffu, d, 2);
+                        d += __shfl_xor_sync(0xffffffffu, d, 4);
+                        if (ch < p.c_in && r < p.rows) contrib = fmaf(d, p.xo[(r * p.t_len + p.t) * p.c_in + ch], contrib);
+                    }
+                    if (c == 0 && r < p.rows) {
+                        const int64_t b = r % p.b_inner;
+                        if (ds_smem) atomicAdd(&tail->s_ds[b], contrib);
+                        else atomicAdd(&p.d_s[b * p.t_len + p.t], contrib);
+                    }
+                }
+            }
+        }
+        // bias / wx gradient partials -> shared accumulators
+#pragma unroll
+        for (int kb = 0; kb < kBwdNkb; ++kb) {
+            const int col = 4 * (kb * 8 + c);
+            atomicAdd(&tail->s_db[col + 0], acc_b[kb].x);
+            atomicAdd(&tail->s_db[col + 1], acc_b[kb].y);
+            atomicAdd(&tail->s_db[col + 2], acc_b[kb].z);
+            atomicAdd(&tail->s_db[col + 3], acc_b[kb].w);
+            if (l0) {
+#pragma unroll
+                for (int ch = 0; ch < kBwdMaxC; ++ch) {
+                    if (ch < p.c_in) {
+                        atomicAdd(&tail->s_dwx[ch * kGateCols + col + 0], acc_x[ch][kb].x);
+                        atomicAdd(&tail->s_dwx[ch * kGateCols + col + 1], acc_x[ch][kb].y);
+                        atomicAdd(&tail->s_dwx[ch * kGateCols + col + 2], acc_x[ch][kb].z);
+                        atomicAdd(&tail->s_dwx[ch * kGateCols + col + 3], acc_x[ch][kb].w);
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        mma_issuer<N, kBwdStages>(bar, smem, Cfg::kStageBytes, Cfg::kBBytes, kBwdNkb, p.n_tiles, tmem_base, lane);
+    } else {
+        // ===================== epilogue: store [dx_below | dh_prev] =====================
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
+            const int a = tcount & 1;
+            const uint32_t aph = (tcount >> 1) & 1;
+            const int64_t r = (int64_t)tile * kTileM + warp * 32 + lane;
+            const bool valid = r < p.rows;
+            mbar_wait(&bar->tmem_full[a], aph);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * N;
+#pragma unroll 1
+            for (int chunk = 0; chunk < N / 32; ++chunk) {
+                uint32_t v[32];
+                tmem_ld32(t_row + chunk * 32, v);
+                tmem_ld_wait();
+                if (valid) {
+                    // columns [0,64) of a 128-wide result are dx_below, the last 64 are dh_prev
+                    const int col = chunk * 32;
+                    float* dst = (N == 128 && col < 64) ? p.dx_out + r * kHid + col
+                                                        : p.dh_rec + r * kHid + (col - (N == 128 ? 64 : 0));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(dst + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bar->tmem_empty[a]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    for (int i = tid; i < kGateCols; i += kBwdThreads) atomicAdd(&p.dbp[i], tail->s_db[i]);
+    if (l0) {
+        for (int i = tid; i < p.c_in * kGateCols; i += kBwdThreads) atomicAdd(&p.dwx[i], tail->s_dwx[i]);
+        if (ds_smem)
+            for (int i = tid; i < (int)p.b_inner; i += kBwdThreads) atomicAdd(&p.d_s[(int64_t)i * p.t_len + p.t], tail->s_ds[i]);
+    }
+}
+
+// Generic K-major hi/lo image of a logical B[n][k] = src[n*rs + k*cs]: per 32-wide k-block [hi | lo], each an
+// [n_rows][32] fp32 tile with the 128-byte swizzle.
+__global__ void pack_image_kernel(const float* __restrict__ src, int n_rows, int k_cols, int64_t rs, int64_t cs,
+                                  float* __restrict__ img) {
+    const int total = n_rows * k_cols;
+    const int tile_floats = n_rows * kKB;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int k = e / kTileN, n = e % kTileN;
-        const float v = wp[e];
+        const int n = e / k_cols, k = e % k_cols;
+        const float v = src[(int64_t)n * rs + (int64_t)k * cs];
         const float hi = tf32_hi(v);
         const float lo = tf32_lo(v, hi);
         const int kb = k / kKB, kk = k % kKB;
         const uint32_t off = sw128_offset((uint32_t)n, (uint32_t)kk) / 4;
-        float* base = img + (size_t)kb * (2 * kBBytes / 4);
+        float* base = img + (size_t)kb * (2 * tile_floats);
         base[off] = hi;
-        base[kBBytes / 4 + off] = lo;
+        base[tile_floats + off] = lo;
     }
 }
 
@@ -275,8 +571,7 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, cons
                             int64_t rows, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        STMGCN_CUDA(cudaFuncSetAttribute(lstm_cell_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemBytes));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_cell_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
         attr_done = true;
     }
     CellParams p;
@@ -299,19 +594,71 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, cons
     p.rows = rows;
     p.n_tiles = (int)ceil_div(rows, kTileM);
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-    lstm_cell_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(p);
+    lstm_cell_tc_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(p);
     count_launch();
     return check_launch("lstm_cell_tc");
 }
 
+// Called from stmgcn_lstm_step_bwd (lstm.cu).  kd = 128 (layers > 0) or 64 (layer 0).
+int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* c_prev, const float* dh_in,
+                           float* dh_rec, float* dc, float* dx_out, const float* wimg_t, float* dbp, const float* wx,
+                           float* dwx, const float* xo, const float* sg, float* d_s, int c_in, int t, int t_len,
+                           int64_t b_inner, int64_t rows, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)BwdCfg<128>::kSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)BwdCfg<64>::kSmem));
+        attr_done = true;
+    }
+    BwdParams p;
+    p.gates = gates;
+    p.c_t = c_t;
+    p.c_prev = c_prev;
+    p.dh_in = dh_in;
+    p.dh_rec = dh_rec;
+    p.dc = dc;
+    p.dx_out = dx_out;
+    p.wimg_t = wimg_t;
+    p.dbp = dbp;
+    p.wx = wx;
+    p.dwx = dwx;
+    p.xo = xo;
+    p.sg = sg;
+    p.d_s = d_s;
+    p.c_in = c_in;
+    p.t = t;
+    p.t_len = t_len;
+    p.b_inner = b_inner;
+    p.rows = rows;
+    p.n_tiles = (int)ceil_div(rows, kTileM);
+    const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+    if (kd == 128)
+        lstm_bwd_tc_kernel<128><<<grid, kBwdThreads, BwdCfg<128>::kSmem, st>>>(p);
+    else
+        lstm_bwd_tc_kernel<64><<<grid, kBwdThreads, BwdCfg<64>::kSmem, st>>>(p);
+    count_launch();
+    return check_launch("lstm_bwd_tc");
+}
+
+int lstm_tc_max_c_bwd() { return kBwdMaxC; }
+
 }  // namespace stmgcn
 
-extern "C" int32_t stmgcn_lstm_pack_tc(const float* wp, int32_t kd, int32_t hid, float* img, void* stream) {
-    STMGCN_REQUIRE(wp && img, STMGCN_ERR_ARG, "lstm_pack_tc: null pointer");
+extern "C" int32_t stmgcn_lstm_pack_tc(const float* wp, int32_t kd, int32_t hid, float* img_fwd, float* img_bwd,
+                                       void* stream) {
+    STMGCN_REQUIRE(wp && img_fwd, STMGCN_ERR_ARG, "lstm_pack_tc: null pointer");
     STMGCN_REQUIRE(hid == kHid && kd > 0 && kd % kKB == 0, STMGCN_ERR_SHAPE,
                    "lstm_pack_tc: tensor-core path needs hid == 64 and kd %% 32 == 0 (got hid=%d kd=%d)", hid, kd);
-    const int total = kd * kTileN;
-    pack_weights_tc_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(wp, kd, img);
+    const int total = kd * kGateCols;
+    cudaStream_t st = (cudaStream_t)stream;
+    // forward operand B[n = gate col][k = kd index] = wp[k][n]
+    pack_image_kernel<<<(total + 255) / 256, 256, 0, st>>>(wp, kGateCols, kd, 1, kGateCols, img_fwd);
     count_launch();
+    if (img_bwd != nullptr) {   // backward operand B[n = kd index][k = gate col] = wp[n][k]
+        pack_image_kernel<<<(total + 255) / 256, 256, 0, st>>>(wp, kd, kGateCols, kGateCols, 1, img_bwd);
+        count_launch();
+    }
     return check_launch("lstm_pack_tc");
 }

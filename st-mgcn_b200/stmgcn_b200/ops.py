@@ -310,19 +310,22 @@ class SharedLSTM(torch.autograd.Function):
         gates = torch.empty((n_layers, t_len, rows, 4 * hid), device=dev, dtype=torch.float32) if need_grad else None
         wp_arr, bp_arr = _lib.ptr_array([w.data_ptr() for w in wp]), _lib.ptr_array([v.data_ptr() for v in bp])
         st = _stream()
-        wimg, wimg_arr = None, None
+        wimg, wimg_t, wimg_arr = None, None, None
         if hid == 64 and lstm_path() == "tc":           # tcgen05 3xTF32 path: pre-swizzled hi/lo weight images
             wimg = [torch.empty(w.shape[0] * 4 * hid * 2, device=dev, dtype=torch.float32) for w in wp]
-            for w, img in zip(wp, wimg):
-                _lib.check(L.stmgcn_lstm_pack_tc(w.data_ptr(), w.shape[0], hid, img.data_ptr(), st), "lstm_pack_tc")
+            wimg_t = [torch.empty_like(v) for v in wimg] if need_grad else [None] * len(wimg)
+            for w, img, img_t in zip(wp, wimg, wimg_t):
+                _lib.check(L.stmgcn_lstm_pack_tc(w.data_ptr(), w.shape[0], hid, img.data_ptr(), _p(img_t), st),
+                           "lstm_pack_tc")
             wimg_arr = _lib.ptr_array([v.data_ptr() for v in wimg])
         for t in range(t_len):
             _lib.check(L.stmgcn_lstm_step_fwd(t, t_len, n_layers, rows, hid, c_in, b, xo.data_ptr(),
                                               s_gate.data_ptr(), wx.data_ptr(), wp_arr, bp_arr, wimg_arr, _p(h0c),
                                               _p(c0c), hs.data_ptr(), cs.data_ptr(), _p(gates), st), "lstm_step_fwd")
         ctx.dims = (n, b, t_len, c_in, n_layers, hid)
+        ctx.tc = wimg is not None
         if need_grad:
-            ctx.save_for_backward(xo, s_gate, h0c, c0c, hs, cs, gates, wx, *wpt)
+            ctx.save_for_backward(xo, s_gate, h0c, c0c, hs, cs, gates, wx, *wpt, *(wimg_t if ctx.tc else []))
         h_top = hs[n_layers - 1, t_len - 1].view(n, b, hid)
         h_n, c_n = hs[:, t_len - 1], cs[:, t_len - 1]
         ctx.mark_non_differentiable(h_n, c_n)
@@ -330,8 +333,10 @@ class SharedLSTM(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_top, _dhn, _dcn):
-        xo, s_gate, h0, c0, hs, cs, gates, wx, *wpt = ctx.saved_tensors
+        xo, s_gate, h0, c0, hs, cs, gates, wx, *rest = ctx.saved_tensors
         n, b, t_len, c_in, n_layers, hid = ctx.dims
+        wpt, wimg_t = rest[:n_layers], rest[n_layers:]
+        wimg_t_arr = _lib.ptr_array([v.data_ptr() for v in wimg_t]) if ctx.tc else None
         rows = n * b
         dev = xo.device
         d_top = _f32c(d_top).view(rows, hid)
@@ -348,7 +353,7 @@ class SharedLSTM(torch.autograd.Function):
         # NOTE: gates is overwritten in place with dA (the tape is consumed; double backward unsupported)
         for t in range(t_len - 1, -1, -1):
             _lib.check(L.stmgcn_lstm_step_bwd(t, t_len, n_layers, rows, hid, c_in, b, xo.data_ptr(),
-                                              s_gate.data_ptr(), wx.data_ptr(), wpt_arr, _p(c0), cs.data_ptr(),
+                                              s_gate.data_ptr(), wx.data_ptr(), wpt_arr, wimg_t_arr, _p(c0), cs.data_ptr(),
                                               gates.data_ptr(), d_top.data_ptr(), dh_rec.data_ptr(),
                                               dc.data_ptr(), dx_work.data_ptr(), d_s.data_ptr(), dwx.data_ptr(),
                                               dbp_arr, st), "lstm_step_bwd")

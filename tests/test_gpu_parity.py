@@ -221,3 +221,35 @@ def test_lstm_tensor_core_path_matches_exact_fp32_path(rows_n, b, t, c):
         ops.set_lstm_path(old)
     for name, a, b_ in zip(("h_top", "h_n", "c_n"), outs["tc"], outs["fma"]):
         assert_close(a.cpu().numpy(), b_.cpu().numpy(), f"tc vs fma {name}", 2e-5)
+
+
+@pytest.mark.parametrize("rows_n,b,t,c", [(5, 60, 3, 1), (40, 64, 4, 1), (3, 50, 2, 2)])
+def test_lstm_tensor_core_backward_matches_exact_fp32_path(rows_n, b, t, c):
+    """tcgen05 fused BPTT kernel (pointwise in the loader + dA.Wp^T) vs the exact-FFMA kernels: d_s and all
+    LSTM weight gradients (C=2 exercises the mixed case: layer 0 on FFMA, layers > 0 on tensor cores)."""
+    from stmgcn_b200 import ops
+    hid, lyr = 64, 3
+    gen = torch.Generator().manual_seed(7 + rows_n)
+    xo = torch.randn(rows_n, b, t, c, generator=gen).to(DEV)
+    s0 = torch.rand(b, t, generator=gen).to(DEV)
+    ws0 = []
+    for l in range(lyr):
+        in_l = c if l == 0 else hid
+        ws0 += [torch.randn(4 * hid, in_l, generator=gen) * 0.2, torch.randn(4 * hid, hid, generator=gen) * 0.2,
+                torch.randn(4 * hid, generator=gen) * 0.1, torch.randn(4 * hid, generator=gen) * 0.1]
+    proj = torch.randn(rows_n, b, hid, generator=gen).to(DEV)
+    res = {}
+    old = ops.lstm_path()
+    try:
+        for path in ("fma", "tc"):
+            ops.set_lstm_path(path)
+            s = s0.clone().requires_grad_(True)
+            ws = [w.to(DEV).requires_grad_(True) for w in ws0]
+            h_top, _, _ = ops.SharedLSTM.apply(xo, s, None, None, lyr, hid, *ws)
+            (h_top * proj).sum().backward()
+            res[path] = [s.grad.clone()] + [w.grad.clone() for w in ws]
+    finally:
+        ops.set_lstm_path(old)
+    names = ["d_s"] + [f"w{i}" for i in range(4 * lyr)]
+    for name, a, b_ in zip(names, res["tc"], res["fma"]):
+        assert_close(a.cpu().numpy(), b_.cpu().numpy(), f"tc vs fma {name}", 5e-5)
