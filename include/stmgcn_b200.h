@@ -145,10 +145,11 @@ int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
                              const float* c0, const float* cs, float* gates, const float* d_top, float* dh_rec,
                              float* dc, float* dx_work, float* d_s, float* dwx, float* const* dbp, void* stream);
 /* weight gradients of one layer after all stmgcn_lstm_step_bwd calls:
- * dwp (kd_l, 4H) += [h_below_t | h_{t-1}]^T dA summed over all (t, r). */
+ * dwp (kd_l, 4H) += [h_below_t | h_{t-1}]^T dA summed over all (t, r).  use_tc != 0 (and H = 64) runs the
+ * tcgen05 3xTF32 kernel, otherwise the exact-FFMA reduction. */
 int32_t stmgcn_lstm_wgrad(int32_t layer, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                           const float* h0, const float* hs, const float* gates_da, float* dwp,
-                          void* stream);
+                          int32_t use_tc, void* stream);
 
 /* ---- fusion over graphs + output FC (STMGCN.py:116-118) ------------------------------------------
  * feat = sum_m g[m] (each (R, G) node-major); y[b, n, c] = feat[n*B+b, :] . fcw[c, :] + fcb[c]. */

@@ -21,6 +21,8 @@ int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* 
                            float* dwx, const float* xo, const float* sg, float* d_s, int c_in, int t, int t_len,
                            int64_t b_inner, int64_t rows, cudaStream_t st);
 int lstm_tc_max_c_bwd();
+int32_t launch_lstm_wgrad_tc(const float* seg0, const float* seg1, const float* h0, const float* da, float* dwp, int kd,
+                             int t_len, int64_t rows, cudaStream_t st);
 }
 
 namespace {
@@ -384,7 +386,7 @@ int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
 
 int32_t stmgcn_lstm_wgrad(int32_t layer, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                           const float* h0, const float* hs, const float* gates_da, float* dwp,
-                          void* stream) {
+                          int32_t use_tc, void* stream) {
     STMGCN_REQUIRE(hs && gates_da && dwp, STMGCN_ERR_ARG, "lstm_wgrad: null pointer");
     STMGCN_REQUIRE(layer >= 0 && layer < n_layers && n_layers <= kMaxLayers && t_len > 0 && rows > 0 && hid > 0 &&
                        hid % 4 == 0,
@@ -392,6 +394,11 @@ int32_t stmgcn_lstm_wgrad(int32_t layer, int32_t t_len, int32_t n_layers, int64_
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t rh = rows * hid;
     const int h4 = 4 * hid;
+    if (use_tc && hid == 64 && aligned16(hs) && aligned16(gates_da) && (!h0 || aligned16(h0)))
+        return launch_lstm_wgrad_tc(layer > 0 ? hs + ((int64_t)(layer - 1) * t_len) * rh : nullptr,
+                                    hs + ((int64_t)layer * t_len) * rh, h0 ? h0 + (int64_t)layer * rh : nullptr,
+                                    gates_da + ((int64_t)layer * t_len) * rows * h4, dwp, layer > 0 ? 128 : 64, t_len,
+                                    rows, st);
     ASegs a{};
     ReduceTime tm{};
     a.segw = hid;

@@ -29,7 +29,8 @@ constexpr int kGateCols = 256;       // 4H
 constexpr int kMaxStages = 3;
 constexpr int kAccs = 2;
 constexpr int kABytes = kTileM * kKB * 4;            // 16 KB per hi or lo A tile
-constexpr int kNumLoaders = 128;
+constexpr int kNumLoaders = 256;     // 8 loader warps
+constexpr int kLoaderWarps = kNumLoaders / 32;
 
 struct Barriers {
     uint64_t full[kMaxStages];
@@ -39,9 +40,9 @@ struct Barriers {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void init_barriers(Barriers* b, int stages, int n_epi_threads) {
+__device__ __forceinline__ void init_barriers(Barriers* b, int stages, int n_epi_threads, int n_loaders) {
     for (int s = 0; s < stages; ++s) {
-        mbar_init(&b->full[s], kNumLoaders + 1);
+        mbar_init(&b->full[s], n_loaders + 1);
         mbar_init(&b->empty[s], 1);
     }
     for (int a = 0; a < kAccs; ++a) {
@@ -109,7 +110,9 @@ constexpr int kFwdStages = 2;
 constexpr int kFwdBBytes = kFwdN * kKB * 4;                       // 32 KB
 constexpr int kFwdStageBytes = 2 * kABytes + 2 * kFwdBBytes;      // 96 KB
 constexpr int kFwdEpiWarps = 8;
-constexpr int kFwdThreads = (kFwdEpiWarps + 4 + 1) * 32;          // 416
+constexpr int kFwdLoaderWarps = 4;                                // 13 warps: 128-register budget per thread
+constexpr int kFwdLoaders = kFwdLoaderWarps * 32;
+constexpr int kFwdThreads = (kFwdEpiWarps + kFwdLoaderWarps + 1) * 32;   // 416
 constexpr int kStagingBytes = 32 * 32 * 4;                        // per epilogue warp: [32 rows][32 cols] fp32
 constexpr int kMaxC = 4;
 
@@ -148,9 +151,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    constexpr int kMmaWarp = kFwdEpiWarps + 4;
+    constexpr int kMmaWarp = kFwdEpiWarps + kFwdLoaderWarps;
 
-    if (tid == 0) init_barriers(bar, kFwdStages, kFwdEpiWarps * 32);
+    if (tid == 0) init_barriers(bar, kFwdStages, kFwdEpiWarps * 32, kFwdLoaders);
     if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, 512);
     for (int i = tid; i < kGateCols; i += kFwdThreads) tail->bias[i] = p.bias[i];
     tc_fence_before();
@@ -159,42 +162,49 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
     const uint32_t tmem_base = bar->tmem_base;
 
     if (warp >= kFwdEpiWarps && warp < kMmaWarp) {
-        // ===================== loaders / tf32 splitters =====================
+        // ===================== loaders / tf32 splitters (register double-buffered) =====================
         const int ltid = tid - kFwdEpiWarps * 32;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int64_t row_base = (int64_t)tile * kTileM;
-            for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-                const int s = it % kFwdStages;
-                const uint32_t ph = (it / kFwdStages) & 1;
-                const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
-                const int koff = (kb & 1) * kKB;
-                float4 v[8];
+        const int c = ltid & 7, rsub = ltid >> 3;          // rows rsub + 16*i, 16-byte chunk c of the 128-byte row
+        auto load = [&](int tile, int kb, float4 (&buf)[8]) {
+            const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
+            const int koff = (kb & 1) * kKB + c * 4;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {            // issue the HBM reads before waiting for the slot
-                    const int idx = ltid + i * kNumLoaders;
-                    const int64_t r = row_base + (idx >> 3);
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (seg != nullptr && r < p.rows)
-                        v[i] = *reinterpret_cast<const float4*>(seg + r * kHid + koff + (idx & 7) * 4);
-                }
-                mbar_wait(&bar->empty[s], ph ^ 1);
-                uint8_t* st = smem + (size_t)s * kFwdStageBytes;
-                if (ltid == 0) {
-                    mbar_arrive_expect_tx(&bar->full[s], 2 * kFwdBBytes);
-                    const float* src = p.wimg + (size_t)kb * (2 * kFwdBBytes / 4);
-                    bulk_g2s(st + 2 * kABytes, src, kFwdBBytes, &bar->full[s]);
-                    bulk_g2s(st + 2 * kABytes + kFwdBBytes, src + kFwdBBytes / 4, kFwdBBytes, &bar->full[s]);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int idx = ltid + i * kNumLoaders;
-                    const int row = idx >> 3, c = idx & 7;
-                    split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), v[i]);
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(&bar->full[s]);
+            for (int i = 0; i < 8; ++i) {
+                const int64_t r = (int64_t)tile * kTileM + rsub + 16 * i;
+                buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (seg != nullptr && r < p.rows) buf[i] = *reinterpret_cast<const float4*>(seg + r * kHid + koff);
             }
+        };
+        uint32_t it = 0;
+        int tile = blockIdx.x, kb = 0;
+        bool have = tile < p.n_tiles;
+        float4 cur[8], nxt[8];
+        if (have) load(tile, kb, cur);
+        while (have) {
+            int ntile = tile, nkb = kb + 1;
+            if (nkb == p.nkb) { nkb = 0; ntile += gridDim.x; }
+            const bool nhave = ntile < p.n_tiles;
+            if (nhave) load(ntile, nkb, nxt);              // next k-block's HBM reads are in flight while we store
+            const int s = it % kFwdStages;
+            const uint32_t ph = (it / kFwdStages) & 1;
+            mbar_wait(&bar->empty[s], ph ^ 1);
+            uint8_t* st = smem + (size_t)s * kFwdStageBytes;
+            if (ltid == 0) {
+                mbar_arrive_expect_tx(&bar->full[s], 2 * kFwdBBytes);
+                const float* src = p.wimg + (size_t)kb * (2 * kFwdBBytes / 4);
+                bulk_g2s(st + 2 * kABytes, src, kFwdBBytes, &bar->full[s]);
+                bulk_g2s(st + 2 * kABytes + kFwdBBytes, src + kFwdBBytes / 4, kFwdBBytes, &bar->full[s]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = rsub + 16 * i;
+                split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), cur[i]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bar->full[s]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+            tile = ntile; kb = nkb; have = nhave; ++it;
         }
     } else if (warp == kMmaWarp) {
         mma_issuer<kFwdN, kFwdStages>(bar, smem, kFwdStageBytes, kFwdBBytes, p.nkb, p.n_tiles, tmem_base, lane);
@@ -218,23 +228,26 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                 for (int c = 0; c < kMaxC; ++c)
                     if (c < p.c_in) xs[c] = p.xo[(r * p.t_len + p.t) * p.c_in + c] * sv;
             }
-            float4 cpa = make_float4(0.f, 0.f, 0.f, 0.f), cpb = cpa;
-            if (p.c_prev != nullptr && valid) {
-                cpa = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + hsel * 32);
-                cpb = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + hsel * 32 + 4);
+            float4 cpv[4];                                  // c_{t-1} for two chunks, prefetched two chunks ahead
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cpv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.c_prev != nullptr && valid)
+                    cpv[j] = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + hsel * 32 + 4 * j);
             }
             mbar_wait(&bar->tmem_full[a], aph);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * kFwdN;
-#pragma unroll 1
+#pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
                 const int chunk = hsel * 4 + ci;                 // 32 gate columns = units [8*chunk, 8*chunk+8)
                 uint32_t v[32];
                 tmem_ld32(t_row + chunk * 32, v);
+                const float4 cpa = cpv[2 * (ci & 1)], cpb = cpv[2 * (ci & 1) + 1];
                 const float cp[8] = {cpa.x, cpa.y, cpa.z, cpa.w, cpb.x, cpb.y, cpb.z, cpb.w};
-                if (ci < 3 && p.c_prev != nullptr && valid) {    // prefetch the next chunk's cell state
-                    cpa = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + (chunk + 1) * 8);
-                    cpb = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + (chunk + 1) * 8 + 4);
+                if (ci < 2 && p.c_prev != nullptr && valid) {
+                    cpv[2 * (ci & 1)] = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + (chunk + 2) * 8);
+                    cpv[2 * (ci & 1) + 1] = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + (chunk + 2) * 8 + 4);
                 }
                 tmem_ld_wait();
                 float hn[8], cn[8];
@@ -306,7 +319,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
 // =====================================================================================================
 constexpr int kBwdStages = 3;
 constexpr int kBwdEpiWarps = 4;
-constexpr int kBwdThreads = (kBwdEpiWarps + 4 + 1) * 32;          // 288
+constexpr int kBwdThreads = (kBwdEpiWarps + kLoaderWarps + 1) * 32;   // 416
 constexpr int kBwdNkb = kGateCols / kKB;                          // 8
 constexpr int kBwdMaxC = 1;                                       // layer-0 TC backward handles input_dim 1
 
@@ -355,11 +368,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    constexpr int kMmaWarp = kBwdEpiWarps + 4;
+    constexpr int kMmaWarp = kBwdEpiWarps + kLoaderWarps;
     constexpr bool l0 = (N == 64);               // layer 0 <=> kd = 64 (no layer below; carries the gate adjoint)
     const bool ds_smem = l0 && p.b_inner <= 2048;
 
-    if (tid == 0) init_barriers(bar, kBwdStages, kBwdEpiWarps * 32);
+    if (tid == 0) init_barriers(bar, kBwdStages, kBwdEpiWarps * 32, kNumLoaders);
     if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, Cfg::kTmemCols);
     for (int i = tid; i < kGateCols; i += kBwdThreads) tail->s_db[i] = 0.f;
     for (int i = tid; i < kBwdMaxC * kGateCols; i += kBwdThreads) tail->s_dwx[i] = 0.f;
@@ -372,130 +385,130 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
 
     if (warp >= kBwdEpiWarps && warp < kMmaWarp) {
         // ===================== loaders: BPTT pointwise -> dA -> operand tiles =====================
+        // thread <-> (unit c of the k-block, rows rsub + 32*i): one LSTM cell per (i, k-block); the reads of the next
+        // k-block are issued into a second register buffer before the current one is processed.
         const int ltid = tid - kBwdEpiWarps * 32;
-        const int c = ltid & 7;                  // unit within the k-block (fixed per thread)
-        const int rsub = ltid >> 3;              // rows rsub + 16*i
-        float4 acc_b[kBwdNkb];
-        float4 acc_x[kBwdMaxC][kBwdNkb];
+        const int c = ltid & 7, rsub = ltid >> 3;
+        struct CellIn { float4 g; float dh, ct, cp, dc; };
+        auto load = [&](int tile, int kb, CellIn (&buf)[4]) {
+            const int unit = kb * 8 + c;
 #pragma unroll
-        for (int kb = 0; kb < kBwdNkb; ++kb) {
-            acc_b[kb] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int ch = 0; ch < kBwdMaxC; ++ch) acc_x[ch][kb] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+            for (int i = 0; i < 4; ++i) {
+                const int64_t r = (int64_t)tile * kTileM + rsub + 32 * i;
+                buf[i].g = make_float4(0.f, 0.f, 0.f, 0.f);
+                buf[i].dh = buf[i].ct = buf[i].cp = buf[i].dc = 0.f;
+                if (r < p.rows) {
+                    const int64_t e = r * kHid + unit;
+                    buf[i].g = *reinterpret_cast<const float4*>(p.gates + r * kGateCols + 4 * unit);
+                    buf[i].dh = p.dh_rec[e] + (p.dh_in ? p.dh_in[e] : 0.f);
+                    buf[i].ct = p.c_t[e];
+                    buf[i].cp = p.c_prev ? p.c_prev[e] : 0.f;
+                    buf[i].dc = p.dc[e];
+                }
+            }
+        };
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        int tile = blockIdx.x, kb = 0;
+        bool have = tile < p.n_tiles;
+        CellIn cur[4], nxt[4];
+        float xs[4], dxs[4];
+        if (have) load(tile, kb, cur);
+        while (have) {
+            int ntile = tile, nkb = kb + 1;
+            if (nkb == kBwdNkb) { nkb = 0; ntile += gridDim.x; }
+            const bool nhave = ntile < p.n_tiles;
+            if (nhave) load(ntile, nkb, nxt);
             const int64_t row_base = (int64_t)tile * kTileM;
-            float xs[8][kBwdMaxC];
-            float dxs[8][kBwdMaxC];
-            if (l0) {
+            const int unit = kb * 8 + c;
+            if (l0 && kb == 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int64_t r = row_base + rsub + 16 * i;
-                    const float sv = (r < p.rows) ? p.sg[(r % p.b_inner) * p.t_len + p.t] : 0.f;
-#pragma unroll
-                    for (int ch = 0; ch < kBwdMaxC; ++ch) {
-                        xs[i][ch] = (ch < p.c_in && r < p.rows) ? p.xo[(r * p.t_len + p.t) * p.c_in + ch] * sv : 0.f;
-                        dxs[i][ch] = 0.f;
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t r = row_base + rsub + 32 * i;
+                    xs[i] = (r < p.rows) ? p.xo[(r * p.t_len + p.t) * p.c_in] * p.sg[(r % p.b_inner) * p.t_len + p.t] : 0.f;
+                    dxs[i] = 0.f;
                 }
             }
+            float4 da[4];
+            float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sx = sb;
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (l0) wv = __ldg(reinterpret_cast<const float4*>(p.wx + 4 * unit));
 #pragma unroll
-            for (int kb = 0; kb < kBwdNkb; ++kb, ++it) {
-                const int s = it % kBwdStages;
-                const uint32_t ph = (it / kBwdStages) & 1;
-                const int unit = kb * 8 + c;
-                float4 da[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int64_t r = row_base + rsub + 16 * i;
-                    da[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < p.rows) {
-                        const int64_t e = r * kHid + unit;
-                        const float4 g = *reinterpret_cast<const float4*>(p.gates + r * kGateCols + 4 * unit);
-                        float dh = p.dh_rec[e];
-                        if (p.dh_in) dh += p.dh_in[e];
-                        const float tc_ = tanhf_(p.c_t[e]);
-                        const float cpv = p.c_prev ? p.c_prev[e] : 0.f;
-                        const float dcv = p.dc[e] + dh * g.w * (1.f - tc_ * tc_);
-                        da[i].x = dcv * g.z * g.x * (1.f - g.x);
-                        da[i].y = dcv * cpv * g.y * (1.f - g.y);
-                        da[i].z = dcv * g.x * (1.f - g.z * g.z);
-                        da[i].w = dh * tc_ * g.w * (1.f - g.w);
-                        p.dc[e] = dcv * g.y;
-                        *reinterpret_cast<float4*>(p.gates + r * kGateCols + 4 * unit) = da[i];
-                        acc_b[kb].x += da[i].x; acc_b[kb].y += da[i].y; acc_b[kb].z += da[i].z; acc_b[kb].w += da[i].w;
-                        if (l0) {
-#pragma unroll
-                            for (int ch = 0; ch < kBwdMaxC; ++ch) {
-                                if (ch < p.c_in) {
-                                    acc_x[ch][kb].x = fmaf(xs[i][ch], da[i].x, acc_x[ch][kb].x);
-                                    acc_x[ch][kb].y = fmaf(xs[i][ch], da[i].y, acc_x[ch][kb].y);
-                                    acc_x[ch][kb].z = fmaf(xs[i][ch], da[i].z, acc_x[ch][kb].z);
-                                    acc_x[ch][kb].w = fmaf(xs[i][ch], da[i].w, acc_x[ch][kb].w);
-                                    const float4 wv = __ldg(reinterpret_cast<const float4*>(p.wx + ch * kGateCols + 4 * unit));
-                                    dxs[i][ch] += da[i].x * wv.x + da[i].y * wv.y + da[i].z * wv.z + da[i].w * wv.w;
-                                }
-                            }
-                        }
-                    }
+            for (int i = 0; i < 4; ++i) {
+                const int64_t r = row_base + rsub + 32 * i;
+                const float4 g = cur[i].g;
+                const float dh = cur[i].dh;
+                const float tc_ = tanhf_(cur[i].ct);
+                const float dcv = cur[i].dc + dh * g.w * (1.f - tc_ * tc_);
+                da[i].x = dcv * g.z * g.x * (1.f - g.x);
+                da[i].y = dcv * cur[i].cp * g.y * (1.f - g.y);
+                da[i].z = dcv * g.x * (1.f - g.z * g.z);
+                da[i].w = dh * tc_ * g.w * (1.f - g.w);
+                if (r < p.rows) {
+                    p.dc[r * kHid + unit] = dcv * g.y;
+                    *reinterpret_cast<float4*>(p.gates + r * kGateCols + 4 * unit) = da[i];
                 }
-                mbar_wait(&bar->empty[s], ph ^ 1);
-                uint8_t* st = smem + (size_t)s * Cfg::kStageBytes;
-                if (ltid == 0) {
-                    mbar_arrive_expect_tx(&bar->full[s], 2 * Cfg::kBBytes);
-                    const float* src = p.wimg_t + (size_t)kb * (2 * Cfg::kBBytes / 4);
-                    bulk_g2s(st + 2 * kABytes, src, Cfg::kBBytes, &bar->full[s]);
-                    bulk_g2s(st + 2 * kABytes + Cfg::kBBytes, src + Cfg::kBBytes / 4, Cfg::kBBytes, &bar->full[s]);
+                sb.x += da[i].x; sb.y += da[i].y; sb.z += da[i].z; sb.w += da[i].w;
+                if (l0) {
+                    sx.x = fmaf(xs[i], da[i].x, sx.x); sx.y = fmaf(xs[i], da[i].y, sx.y);
+                    sx.z = fmaf(xs[i], da[i].z, sx.z); sx.w = fmaf(xs[i], da[i].w, sx.w);
+                    dxs[i] += da[i].x * wv.x + da[i].y * wv.y + da[i].z * wv.z + da[i].w * wv.w;
                 }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = rsub + 16 * i;
-                    split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), da[i]);
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(&bar->full[s]);
             }
-            if (l0) {     // gate adjoint: d s[b,t] += sum_c dxmod[r,c] * xo[r,t,c]  (STMGCN.py:44)
+            // bias (and layer-0 input-weight) gradient partials: reduce over the 4 lanes that share this unit,
+            // then one shared-memory atomic per value
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int64_t r = row_base + rsub + 16 * i;
-                    float contrib = 0.f;
+            for (int o = 8; o <= 16; o <<= 1) {
+                sb.x += __shfl_xor_sync(0xffffffffu, sb.x, o); sb.y += __shfl_xor_sync(0xffffffffu, sb.y, o);
+                sb.z += __shfl_xor_sync(0xffffffffu, sb.z, o); sb.w += __shfl_xor_sync(0xffffffffu, sb.w, o);
+                if (l0) {
+                    sx.x += __shfl_xor_sync(0xffffffffu, sx.x, o); sx.y += __shfl_xor_sync(0xffffffffu, sx.y, o);
+                    sx.z += __shfl_xor_sync(0xffffffffu, sx.z, o); sx.w += __shfl_xor_sync(0xffffffffu, sx.w, o);
+                }
+            }
+            if (lane < 8) {
+                atomicAdd(&tail->s_db[4 * unit + 0], sb.x); atomicAdd(&tail->s_db[4 * unit + 1], sb.y);
+                atomicAdd(&tail->s_db[4 * unit + 2], sb.z); atomicAdd(&tail->s_db[4 * unit + 3], sb.w);
+                if (l0) {
+                    atomicAdd(&tail->s_dwx[4 * unit + 0], sx.x); atomicAdd(&tail->s_dwx[4 * unit + 1], sx.y);
+                    atomicAdd(&tail->s_dwx[4 * unit + 2], sx.z); atomicAdd(&tail->s_dwx[4 * unit + 3], sx.w);
+                }
+            }
+            const int s = it % kBwdStages;
+            const uint32_t ph = (it / kBwdStages) & 1;
+            mbar_wait(&bar->empty[s], ph ^ 1);
+            uint8_t* st = smem + (size_t)s * Cfg::kStageBytes;
+            if (ltid == 0) {
+                mbar_arrive_expect_tx(&bar->full[s], 2 * Cfg::kBBytes);
+                const float* src = p.wimg_t + (size_t)kb * (2 * Cfg::kBBytes / 4);
+                bulk_g2s(st + 2 * kABytes, src, Cfg::kBBytes, &bar->full[s]);
+                bulk_g2s(st + 2 * kABytes + Cfg::kBBytes, src + Cfg::kBBytes / 4, Cfg::kBBytes, &bar->full[s]);
+            }
 #pragma unroll
-                    for (int ch = 0; ch < kBwdMaxC; ++ch) {
-                        float d = dxs[i][ch];
-                        d += __shfl_xor_sync(0xffffffffu, d, 1);
-                        d += __shfl_xor_sync(0xffffffffu, d, 2);
-                        d += __shfl_xor_sync(0xffffffffu, d, 4);
-                        if (ch < p.c_in && r < p.rows) contrib = fmaf(d, p.xo[(r * p.t_len + p.t) * p.c_in + ch], contrib);
-                    }
+            for (int i = 0; i < 4; ++i) {
+                const int row = rsub + 32 * i;
+                split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), da[i]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bar->full[s]);
+            if (l0 && kb == kBwdNkb - 1) {     // gate adjoint: d s[b,t] += dxmod[r] * xo[r,t]   (STMGCN.py:44, C = 1)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t r = row_base + rsub + 32 * i;
+                    float d = dxs[i];
+                    d += __shfl_xor_sync(0xffffffffu, d, 1);
+                    d += __shfl_xor_sync(0xffffffffu, d, 2);
+                    d += __shfl_xor_sync(0xffffffffu, d, 4);
                     if (c == 0 && r < p.rows) {
+                        const float contrib = d * p.xo[(r * p.t_len + p.t) * p.c_in];
                         const int64_t b = r % p.b_inner;
                         if (ds_smem) atomicAdd(&tail->s_ds[b], contrib);
                         else atomicAdd(&p.d_s[b * p.t_len + p.t], contrib);
                     }
                 }
             }
-        }
-        // bias / wx gradient partials -> shared accumulators
 #pragma unroll
-        for (int kb = 0; kb < kBwdNkb; ++kb) {
-            const int col = 4 * (kb * 8 + c);
-            atomicAdd(&tail->s_db[col + 0], acc_b[kb].x);
-            atomicAdd(&tail->s_db[col + 1], acc_b[kb].y);
-            atomicAdd(&tail->s_db[col + 2], acc_b[kb].z);
-            atomicAdd(&tail->s_db[col + 3], acc_b[kb].w);
-            if (l0) {
-#pragma unroll
-                for (int ch = 0; ch < kBwdMaxC; ++ch) {
-                    if (ch < p.c_in) {
-                        atomicAdd(&tail->s_dwx[ch * kGateCols + col + 0], acc_x[ch][kb].x);
-                        atomicAdd(&tail->s_dwx[ch * kGateCols + col + 1], acc_x[ch][kb].y);
-                        atomicAdd(&tail->s_dwx[ch * kGateCols + col + 2], acc_x[ch][kb].z);
-                        atomicAdd(&tail->s_dwx[ch * kGateCols + col + 3], acc_x[ch][kb].w);
-                    }
-                }
-            }
+            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+            tile = ntile; kb = nkb; have = nhave; ++it;
         }
     } else if (warp == kMmaWarp) {
         mma_issuer<N, kBwdStages>(bar, smem, Cfg::kStageBytes, Cfg::kBBytes, kBwdNkb, p.n_tiles, tmem_base, lane);
@@ -539,6 +552,182 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
         if (ds_smem)
             for (int i = tid; i < (int)p.b_inner; i += kBwdThreads) atomicAdd(&p.d_s[(int64_t)i * p.t_len + p.t], tail->s_ds[i]);
     }
+}
+
+// =====================================================================================================
+// weight gradients:  dWp[kd x 256] += sum over (t, r) of [h_below_t | h_{t-1}][r, :]^T . dA_t[r, :]
+// M = kd index (padded to 128), N = 256 gate columns, K = rows.  Both operands are row-major in HBM (K is the slow
+// dimension); the loaders transpose them while writing shared memory -- lane <-> row, so the scalar stores of a
+// warp hit 32 different banks -- into the same K-major 128B-swizzled tiles the other kernels use.  (Setting the
+// MN-major bits of the tf32 instruction descriptor produced all-zero accumulators on B200 in our tests, so the
+// transposition is done in software.)  One TMEM accumulator lives for the whole kernel and is flushed with red.add.
+// =====================================================================================================
+constexpr int kWgStages = 2;
+constexpr int kWgRows = 32;                                        // K per stage
+constexpr int kWgABytes = 128 * kWgRows * 4;                       // 16 KB  [128 m][32 k] K-major
+constexpr int kWgBBytes = 256 * kWgRows * 4;                       // 32 KB  [256 n][32 k] K-major
+constexpr int kWgStageBytes = 2 * kWgABytes + 2 * kWgBBytes;       // 96 KB
+constexpr int kWgLoaderWarps = 8;
+constexpr int kWgThreads = (kWgLoaderWarps + 1) * 32;              // 288
+
+struct WgTail {
+    uint64_t full[kWgStages];
+    uint64_t empty[kWgStages];
+    uint64_t done;
+    uint32_t tmem_base;
+};
+constexpr size_t kWgSmem = 1024 + (size_t)kWgStages * kWgStageBytes + sizeof(WgTail);
+
+struct WgParams {
+    const float* seg0;       // h_below tape base for this layer: (T, rows, 64) or nullptr (layer 0)
+    const float* seg1;       // this layer's h tape base (T, rows, 64): read shifted by one step
+    const float* h0;         // (rows, 64) value of h_{-1} or nullptr (zeros)
+    const float* da;         // (T, rows, 256)
+    float* dwp;              // (kd, 256) +=
+    int kd;                  // 128 or 64 (layer 0: only seg1)
+    int t_len;
+    int64_t rows;
+    int64_t chunks_per_t;    // ceil(rows / 32)
+    int64_t total_chunks;
+};
+
+// transpose-store one float4 (4 consecutive M/N indices mn..mn+3 of row k) into a K-major swizzled tile pair
+__device__ __forceinline__ void split_store_t(uint8_t* hi_tile, uint8_t* lo_tile, int mn, int k, const float4& v) {
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t off = sw128_offset((uint32_t)(mn + j), (uint32_t)k);
+        const float hi = tf32_hi(vv[j]);
+        *reinterpret_cast<float*>(hi_tile + off) = hi;
+        *reinterpret_cast<float*>(lo_tile + off) = tf32_lo(vv[j], hi);
+    }
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    WgTail* tail = (WgTail*)(smem + (size_t)kWgStages * kWgStageBytes);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    constexpr int kMmaWarp = kWgLoaderWarps;
+    constexpr int kLoaders = kWgLoaderWarps * 32;
+
+    if (tid == 0) {
+        for (int s = 0; s < kWgStages; ++s) {
+            mbar_init(&tail->full[s], kLoaders);
+            mbar_init(&tail->empty[s], 1);
+        }
+        mbar_init(&tail->done, 1);
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+    const bool has_work = (int64_t)blockIdx.x < p.total_chunks;
+
+    if (warp < kMmaWarp) {
+        // ===================== loaders: HBM rows -> tf32 hi/lo -> MN-major swizzled atoms =====================
+        const int ltid = tid;
+        struct Buf { float4 a[4]; float4 b[8]; };
+        auto load = [&](int64_t chunk, Buf& buf) {
+            const int t = (int)(chunk / p.chunks_per_t);
+            const int64_t r0 = (chunk % p.chunks_per_t) * kWgRows;
+            const float* s0 = p.seg0 ? p.seg0 + (int64_t)t * p.rows * kHid : nullptr;
+            const float* s1 = (t > 0) ? p.seg1 + (int64_t)(t - 1) * p.rows * kHid : p.h0;
+            const float* dt = p.da + (int64_t)t * p.rows * kGateCols;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = ltid & 31, q = (ltid >> 5) + 8 * i;      // lane <-> row (K index), q: float4 along M
+                const int64_t r = r0 + row;
+                // kd = 128: m 0..63 from seg0 (h_below), 64..127 from seg1 (h_prev); kd = 64: m 0..63 from seg1
+                const float* src = (p.kd == 128) ? (q < 16 ? s0 : s1) : (q < 16 ? s1 : nullptr);
+                buf.a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src != nullptr && r < p.rows) buf.a[i] = *reinterpret_cast<const float4*>(src + r * kHid + (q & 15) * 4);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = ltid & 31, q = (ltid >> 5) + 8 * i;      // q: float4 along N (64 per row)
+                const int64_t r = r0 + row;
+                buf.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < p.rows) buf.b[i] = *reinterpret_cast<const float4*>(dt + r * kGateCols + q * 4);
+            }
+        };
+        uint32_t it = 0;
+        int64_t chunk = blockIdx.x;
+        bool have = chunk < p.total_chunks;
+        Buf cur, nxt;
+        if (have) load(chunk, cur);
+        while (have) {
+            const int64_t nchunk = chunk + gridDim.x;
+            const bool nhave = nchunk < p.total_chunks;
+            if (nhave) load(nchunk, nxt);
+            const int s = it % kWgStages;
+            const uint32_t ph = (it / kWgStages) & 1;
+            mbar_wait(&tail->empty[s], ph ^ 1);
+            uint8_t* st = smem + (size_t)s * kWgStageBytes;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                split_store_t(st, st + kWgABytes, 4 * ((ltid >> 5) + 8 * i), ltid & 31, cur.a[i]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                split_store_t(st + 2 * kWgABytes, st + 2 * kWgABytes + kWgBBytes, 4 * ((ltid >> 5) + 8 * i), ltid & 31, cur.b[i]);
+            fence_proxy_async_smem();
+            mbar_arrive(&tail->full[s]);
+            cur = nxt;
+            chunk = nchunk; have = nhave; ++it;
+        }
+        // ===================== epilogue (warps 0-3): accumulator rows = kd index -> red.add into dWp =====================
+        if (warp < 4 && has_work) {
+            mbar_wait(&tail->done, 0);
+            tc_fence_after();
+            const int m = warp * 32 + lane;
+            const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int chunk32 = 0; chunk32 < kGateCols / 32; ++chunk32) {
+                uint32_t v[32];
+                tmem_ld32(t_row + chunk32 * 32, v);
+                tmem_ld_wait();
+                if (m < p.kd) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(p.dwp + (int64_t)m * kGateCols + chunk32 * 32 + j, __uint_as_float(v[j]));
+                }
+            }
+        }
+    } else {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = idesc_tf32(128, kGateCols);
+        uint32_t it = 0;
+        for (int64_t chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x, ++it) {
+            const int s = it % kWgStages;
+            const uint32_t ph = (it / kWgStages) & 1;
+            mbar_wait(&tail->full[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = smem_u32(smem + (size_t)s * kWgStageBytes);
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a_base = st + ((pass == 1) ? kWgABytes : 0);
+                    const uint32_t b_base = st + 2 * kWgABytes + ((pass == 2) ? kWgBBytes : 0);
+#pragma unroll
+                    const uint64_t da = smem_desc_k_sw128(a_base), db = smem_desc_k_sw128(b_base);
+                    for (int ks = 0; ks < kWgRows / 8; ++ks)
+                        mma_tf32(tmem_base, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc,
+                                 (it > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+                }
+                mma_commit(&tail->empty[s]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && has_work) mma_commit(&tail->done);
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 256);
 }
 
 // Generic K-major hi/lo image of a logical B[n][k] = src[n*rs + k*cs]: per 32-wide k-block [hi | lo], each an
@@ -643,6 +832,31 @@ int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* 
 }
 
 int lstm_tc_max_c_bwd() { return kBwdMaxC; }
+
+// Called from stmgcn_lstm_wgrad (lstm.cu).
+int32_t launch_lstm_wgrad_tc(const float* seg0, const float* seg1, const float* h0, const float* da, float* dwp, int kd,
+                             int t_len, int64_t rows, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem));
+        attr_done = true;
+    }
+    WgParams p;
+    p.seg0 = seg0;
+    p.seg1 = seg1;
+    p.h0 = h0;
+    p.da = da;
+    p.dwp = dwp;
+    p.kd = kd;
+    p.t_len = t_len;
+    p.rows = rows;
+    p.chunks_per_t = ceil_div(rows, kWgRows);
+    p.total_chunks = p.chunks_per_t * t_len;
+    const int64_t grid = p.total_chunks < sm_count() ? p.total_chunks : sm_count();
+    lstm_wgrad_tc_kernel<<<(unsigned)grid, kWgThreads, kWgSmem, st>>>(p);
+    count_launch();
+    return check_launch("lstm_wgrad_tc");
+}
 
 }  // namespace stmgcn
 

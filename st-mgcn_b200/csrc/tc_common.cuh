@@ -120,14 +120,26 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B [61,64)
     return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M x N tile
-__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n) {
-    return (1u << 4)               // c_format  = F32
-           | (2u << 7)             // a_format  = TF32
-           | (2u << 10)            // b_format  = TF32
-           | (0u << 15)            // a_major   = K
-           | (0u << 16)            // b_major   = K
+// kind::tf32, fp32 accumulate, M x N tile; mn_major = 0: A and B K-major, 1: both MN-major
+__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, int mn_major = 0) {
+    return (1u << 4)                               // c_format  = F32
+           | (2u << 7)                             // a_format  = TF32
+           | (2u << 10)                            // b_format  = TF32
+           | ((uint32_t)(mn_major & 1) << 15)      // a_major
+           | ((uint32_t)(mn_major & 1) << 16)      // b_major
            | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// MN-major operand, 128-byte swizzle.  Canonical layout (cute/atom/mma_traits_sm100.hpp, in 16-byte units):
+// ((8,n),(8,k)) : ((1,LBO),(8,SBO)) -- a 1024-byte atom holds 32 consecutive M/N elements (one 128-byte row)
+// for each of 8 consecutive K; LBO = byte distance between atoms along M/N, SBO = between atoms along K.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
 }
 
 // byte offset of element (row, k) inside a [rows][32 fp32] K-major tile with the 128-byte swizzle

@@ -359,7 +359,7 @@ class SharedLSTM(torch.autograd.Function):
                                               dbp_arr, st), "lstm_step_bwd")
         for l in range(n_layers):
             _lib.check(L.stmgcn_lstm_wgrad(l, t_len, n_layers, rows, hid, _p(h0), hs.data_ptr(), gates.data_ptr(),
-                                           dwp[l].data_ptr(), st), "lstm_wgrad")
+                                           dwp[l].data_ptr(), int(ctx.tc), st), "lstm_wgrad")
         w_grads = _unpack_lstm_grads(dwx, dwp, dbp, n_layers, hid, c_in)
         return (None, d_s, None, None, None, None, *w_grads)
 
