@@ -29,7 +29,7 @@ constexpr int kGateCols = 256;       // 4H
 constexpr int kMaxStages = 3;
 constexpr int kAccs = 2;
 constexpr int kABytes = kTileM * kKB * 4;            // 16 KB per hi or lo A tile
-constexpr int kNumLoaders = 256;     // 8 loader warps
+constexpr int kNumLoaders = 512;     // 16 loader warps (backward): the loaders are latency-bound, TLP is what helps
 constexpr int kLoaderWarps = kNumLoaders / 32;
 
 struct Barriers {
@@ -53,21 +53,22 @@ __device__ __forceinline__ void init_barriers(Barriers* b, int stages, int n_epi
 }
 
 // The MMA warp: for every tile, for every k-block: wait operands, issue 3 x 4 MMAs, release the stage.
-template <int N, int STAGES>
+template <int N, int STAGES, int PROF_KERNEL>
 __device__ __forceinline__ void mma_issuer(Barriers* bar, uint8_t* smem, int stage_bytes, int b_bytes, int nkb,
                                            int n_tiles, uint32_t tmem_base, int lane) {
     constexpr uint32_t idesc = idesc_tf32(kTileM, N);
+    TC_PROF_DECL
     uint32_t it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         const int a = tcount & 1;
         const uint32_t aph = (tcount >> 1) & 1;
-        mbar_wait(&bar->tmem_empty[a], aph ^ 1);
+        mbar_wait(&bar->tmem_empty[a], aph ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)a * N;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&bar->full[s], ph);
+            mbar_wait(&bar->full[s], ph, 1);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
@@ -92,6 +93,7 @@ __device__ __forceinline__ void mma_issuer(Barriers* bar, uint8_t* smem, int sta
         if (lane == 0) mma_commit(&bar->tmem_full[a]);
         __syncwarp();
     }
+    TC_PROF_FLUSH(PROF_KERNEL * 3 + 1, lane == 0)
 }
 
 __device__ __forceinline__ void split_store(uint8_t* st, uint32_t off, const float4& v) {
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
 
     if (warp >= kFwdEpiWarps && warp < kMmaWarp) {
         // ===================== loaders / tf32 splitters (register double-buffered) =====================
+        TC_PROF_DECL
         const int ltid = tid - kFwdEpiWarps * 32;
         const int c = ltid & 7, rsub = ltid >> 3;          // rows rsub + 16*i, 16-byte chunk c of the 128-byte row
         auto load = [&](int tile, int kb, float4 (&buf)[8]) {
@@ -176,18 +179,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
             }
         };
         uint32_t it = 0;
-        int tile = blockIdx.x, kb = 0;
-        bool have = tile < p.n_tiles;
-        float4 cur[8], nxt[8];
-        if (have) load(tile, kb, cur);
-        while (have) {
-            int ntile = tile, nkb = kb + 1;
-            if (nkb == p.nkb) { nkb = 0; ntile += gridDim.x; }
-            const bool nhave = ntile < p.n_tiles;
-            if (nhave) load(ntile, nkb, nxt);              // next k-block's HBM reads are in flight while we store
+        auto process = [&](const float4 (&cur)[8], int kb) {
             const int s = it % kFwdStages;
             const uint32_t ph = (it / kFwdStages) & 1;
-            mbar_wait(&bar->empty[s], ph ^ 1);
+            mbar_wait(&bar->empty[s], ph ^ 1, 0);
             uint8_t* st = smem + (size_t)s * kFwdStageBytes;
             if (ltid == 0) {
                 mbar_arrive_expect_tx(&bar->full[s], 2 * kFwdBBytes);
@@ -202,14 +197,32 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
             }
             fence_proxy_async_smem();
             mbar_arrive(&bar->full[s]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-            tile = ntile; kb = nkb; have = nhave; ++it;
+            ++it;
+        };
+        // ping-pong between two register buffers (no copies: a copy would wait for the prefetch it is hiding)
+        int tile = blockIdx.x, kb = 0;
+        bool have = tile < p.n_tiles;
+        float4 b0[8], b1[8];
+        if (have) load(tile, kb, b0);
+        while (have) {
+            int ck = kb;
+            if (++kb == p.nkb) { kb = 0; tile += gridDim.x; }
+            have = tile < p.n_tiles;
+            if (have) load(tile, kb, b1);
+            process(b0, ck);
+            if (!have) break;
+            ck = kb;
+            if (++kb == p.nkb) { kb = 0; tile += gridDim.x; }
+            have = tile < p.n_tiles;
+            if (have) load(tile, kb, b0);
+            process(b1, ck);
         }
+        TC_PROF_FLUSH(0, ltid == 0)
     } else if (warp == kMmaWarp) {
-        mma_issuer<kFwdN, kFwdStages>(bar, smem, kFwdStageBytes, kFwdBBytes, p.nkb, p.n_tiles, tmem_base, lane);
+        mma_issuer<kFwdN, kFwdStages, 0>(bar, smem, kFwdStageBytes, kFwdBBytes, p.nkb, p.n_tiles, tmem_base, lane);
     } else {
         // ===================== epilogue: LSTM cell (8 warps: TMEM lane quadrant q, column half hsel) ============
+        TC_PROF_DECL
         const int q = warp & 3, hsel = warp >> 2;
         float* stg = reinterpret_cast<float*>(staging + (size_t)warp * kStagingBytes);
         uint32_t tcount = 0;
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                 if (p.c_prev != nullptr && valid)
                     cpv[j] = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + hsel * 32 + 4 * j);
             }
-            mbar_wait(&bar->tmem_full[a], aph);
+            mbar_wait(&bar->tmem_full[a], aph, 3);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * kFwdN;
 #pragma unroll
@@ -307,6 +320,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
             tc_fence_before();
             mbar_arrive(&bar->tmem_empty[a]);
         }
+        TC_PROF_FLUSH(2, tid == 0)
     }
     tc_fence_before();
     __syncthreads();
@@ -323,14 +337,16 @@ constexpr int kBwdThreads = (kBwdEpiWarps + kLoaderWarps + 1) * 32;   // 416
 constexpr int kBwdNkb = kGateCols / kKB;                          // 8
 constexpr int kBwdMaxC = 1;                                       // layer-0 TC backward handles input_dim 1
 
-struct BwdTail {
-    float s_db[kGateCols];
-    float s_dwx[kBwdMaxC * kGateCols];
-    float s_ds[2048];
+template <int N>
+struct BwdTailT {
+    float s_db[kLoaderWarps][kGateCols];                        // per-loader-warp private partial sums
+    float s_dwx[N == 64 ? kLoaderWarps : 1][kGateCols];         // layer 0 only (input_dim == 1)
+    float s_ds[N == 64 ? 2048 : 1];                             // layer 0 only
     Barriers bar;
 };
 template <int N>
 struct BwdCfg {
+    using BwdTail = BwdTailT<N>;
     static constexpr int kBBytes = N * kKB * 4;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
     static constexpr size_t kSmem = 1024 + (size_t)kBwdStages * kStageBytes + sizeof(BwdTail);
@@ -363,6 +379,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
     using Cfg = BwdCfg<N>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    using BwdTail = typename Cfg::BwdTail;
     BwdTail* tail = (BwdTail*)(smem + (size_t)kBwdStages * Cfg::kStageBytes);
     Barriers* bar = &tail->bar;
     const int tid = threadIdx.x;
@@ -374,8 +391,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
 
     if (tid == 0) init_barriers(bar, kBwdStages, kBwdEpiWarps * 32, kNumLoaders);
     if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, Cfg::kTmemCols);
-    for (int i = tid; i < kGateCols; i += kBwdThreads) tail->s_db[i] = 0.f;
-    for (int i = tid; i < kBwdMaxC * kGateCols; i += kBwdThreads) tail->s_dwx[i] = 0.f;
+    for (int i = tid; i < kLoaderWarps * kGateCols; i += kBwdThreads) {
+        (&tail->s_db[0][0])[i] = 0.f;
+        if (l0) (&tail->s_dwx[0][0])[i] = 0.f;
+    }
     if (ds_smem)
         for (int i = tid; i < (int)p.b_inner; i += kBwdThreads) tail->s_ds[i] = 0.f;
     tc_fence_before();
@@ -385,22 +404,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
 
     if (warp >= kBwdEpiWarps && warp < kMmaWarp) {
         // ===================== loaders: BPTT pointwise -> dA -> operand tiles =====================
-        // thread <-> (unit c of the k-block, rows rsub + 32*i): one LSTM cell per (i, k-block); the reads of the next
+        // thread <-> (unit c of the k-block, rows rsub + kRowStep*i): one LSTM cell per (i, k-block); the reads of the next
         // k-block are issued into a second register buffer before the current one is processed.
+        TC_PROF_DECL
         const int ltid = tid - kBwdEpiWarps * 32;
-        const int c = ltid & 7, rsub = ltid >> 3;
-        struct CellIn { float4 g; float dh, ct, cp, dc; };
-        auto load = [&](int tile, int kb, CellIn (&buf)[4]) {
+        const int c = ltid & 7, rsub = ltid >> 3, lwarp = ltid >> 5;
+        constexpr int kCells = kTileM * 8 / kNumLoaders;      // LSTM cells per thread per k-block
+        constexpr int kRowStep = kNumLoaders / 8;
+        struct CellIn { float4 g; float dh, dh2, ct, cp, dc; };   // raw loads only: no arithmetic before use
+        auto load = [&](int tile, int kb, CellIn (&buf)[kCells]) {
             const int unit = kb * 8 + c;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t r = (int64_t)tile * kTileM + rsub + 32 * i;
+            for (int i = 0; i < kCells; ++i) {
+                const int64_t r = (int64_t)tile * kTileM + rsub + kRowStep * i;
                 buf[i].g = make_float4(0.f, 0.f, 0.f, 0.f);
-                buf[i].dh = buf[i].ct = buf[i].cp = buf[i].dc = 0.f;
+                buf[i].dh = buf[i].dh2 = buf[i].ct = buf[i].cp = buf[i].dc = 0.f;
                 if (r < p.rows) {
                     const int64_t e = r * kHid + unit;
                     buf[i].g = *reinterpret_cast<const float4*>(p.gates + r * kGateCols + 4 * unit);
-                    buf[i].dh = p.dh_rec[e] + (p.dh_in ? p.dh_in[e] : 0.f);
+                    buf[i].dh = p.dh_rec[e];
+                    if (p.dh_in) buf[i].dh2 = p.dh_in[e];
                     buf[i].ct = p.c_t[e];
                     buf[i].cp = p.c_prev ? p.c_prev[e] : 0.f;
                     buf[i].dc = p.dc[e];
@@ -408,35 +431,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
             }
         };
         uint32_t it = 0;
-        int tile = blockIdx.x, kb = 0;
-        bool have = tile < p.n_tiles;
-        CellIn cur[4], nxt[4];
-        float xs[4], dxs[4];
-        if (have) load(tile, kb, cur);
-        while (have) {
-            int ntile = tile, nkb = kb + 1;
-            if (nkb == kBwdNkb) { nkb = 0; ntile += gridDim.x; }
-            const bool nhave = ntile < p.n_tiles;
-            if (nhave) load(ntile, nkb, nxt);
+        float xs[kCells], dxs[kCells];
+        auto process = [&](const CellIn (&cur)[kCells], int tile, int kb) {
             const int64_t row_base = (int64_t)tile * kTileM;
             const int unit = kb * 8 + c;
             if (l0 && kb == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t r = row_base + rsub + 32 * i;
+                for (int i = 0; i < kCells; ++i) {
+                    const int64_t r = row_base + rsub + kRowStep * i;
                     xs[i] = (r < p.rows) ? p.xo[(r * p.t_len + p.t) * p.c_in] * p.sg[(r % p.b_inner) * p.t_len + p.t] : 0.f;
                     dxs[i] = 0.f;
                 }
             }
-            float4 da[4];
+            float4 da[kCells];
             float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sx = sb;
             float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (l0) wv = __ldg(reinterpret_cast<const float4*>(p.wx + 4 * unit));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t r = row_base + rsub + 32 * i;
+            for (int i = 0; i < kCells; ++i) {
+                const int64_t r = row_base + rsub + kRowStep * i;
                 const float4 g = cur[i].g;
-                const float dh = cur[i].dh;
+                const float dh = cur[i].dh + cur[i].dh2;
                 const float tc_ = tanhf_(cur[i].ct);
                 const float dcv = cur[i].dc + dh * g.w * (1.f - tc_ * tc_);
                 da[i].x = dcv * g.z * g.x * (1.f - g.x);
@@ -465,17 +480,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
                     sx.z += __shfl_xor_sync(0xffffffffu, sx.z, o); sx.w += __shfl_xor_sync(0xffffffffu, sx.w, o);
                 }
             }
-            if (lane < 8) {
-                atomicAdd(&tail->s_db[4 * unit + 0], sb.x); atomicAdd(&tail->s_db[4 * unit + 1], sb.y);
-                atomicAdd(&tail->s_db[4 * unit + 2], sb.z); atomicAdd(&tail->s_db[4 * unit + 3], sb.w);
+            if (lane < 8) {        // lanes 0-7 own units c = 0..7 of this warp's private accumulator row
+                float4* acc = reinterpret_cast<float4*>(&tail->s_db[lwarp][4 * unit]);
+                float4 t = *acc;
+                t.x += sb.x; t.y += sb.y; t.z += sb.z; t.w += sb.w;
+                *acc = t;
                 if (l0) {
-                    atomicAdd(&tail->s_dwx[4 * unit + 0], sx.x); atomicAdd(&tail->s_dwx[4 * unit + 1], sx.y);
-                    atomicAdd(&tail->s_dwx[4 * unit + 2], sx.z); atomicAdd(&tail->s_dwx[4 * unit + 3], sx.w);
+                    float4* accx = reinterpret_cast<float4*>(&tail->s_dwx[l0 ? lwarp : 0][4 * unit]);
+                    float4 tx = *accx;
+                    tx.x += sx.x; tx.y += sx.y; tx.z += sx.z; tx.w += sx.w;
+                    *accx = tx;
                 }
             }
             const int s = it % kBwdStages;
             const uint32_t ph = (it / kBwdStages) & 1;
-            mbar_wait(&bar->empty[s], ph ^ 1);
+            mbar_wait(&bar->empty[s], ph ^ 1, 0);
             uint8_t* st = smem + (size_t)s * Cfg::kStageBytes;
             if (ltid == 0) {
                 mbar_arrive_expect_tx(&bar->full[s], 2 * Cfg::kBBytes);
@@ -484,16 +503,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
                 bulk_g2s(st + 2 * kABytes + Cfg::kBBytes, src + Cfg::kBBytes / 4, Cfg::kBBytes, &bar->full[s]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = rsub + 32 * i;
+            for (int i = 0; i < kCells; ++i) {
+                const int row = rsub + kRowStep * i;
                 split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), da[i]);
             }
             fence_proxy_async_smem();
             mbar_arrive(&bar->full[s]);
             if (l0 && kb == kBwdNkb - 1) {     // gate adjoint: d s[b,t] += dxmod[r] * xo[r,t]   (STMGCN.py:44, C = 1)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t r = row_base + rsub + 32 * i;
+                for (int i = 0; i < kCells; ++i) {
+                    const int64_t r = row_base + rsub + kRowStep * i;
                     float d = dxs[i];
                     d += __shfl_xor_sync(0xffffffffu, d, 1);
                     d += __shfl_xor_sync(0xffffffffu, d, 2);
@@ -506,21 +525,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
                     }
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-            tile = ntile; kb = nkb; have = nhave; ++it;
+            ++it;
+        };
+        int tile = blockIdx.x, kb = 0;
+        bool have = tile < p.n_tiles;
+        CellIn b0[kCells], b1[kCells];
+        if (have) load(tile, kb, b0);
+        while (have) {
+            int ct = tile, ck = kb;
+            if (++kb == kBwdNkb) { kb = 0; tile += gridDim.x; }
+            have = tile < p.n_tiles;
+            if (have) load(tile, kb, b1);
+            process(b0, ct, ck);
+            if (!have) break;
+            ct = tile; ck = kb;
+            if (++kb == kBwdNkb) { kb = 0; tile += gridDim.x; }
+            have = tile < p.n_tiles;
+            if (have) load(tile, kb, b0);
+            process(b1, ct, ck);
         }
+        TC_PROF_FLUSH((N == 128 ? 3 : 6), ltid == 0)
     } else if (warp == kMmaWarp) {
-        mma_issuer<N, kBwdStages>(bar, smem, Cfg::kStageBytes, Cfg::kBBytes, kBwdNkb, p.n_tiles, tmem_base, lane);
+        mma_issuer<N, kBwdStages, (N == 128 ? 1 : 2)>(bar, smem, Cfg::kStageBytes, Cfg::kBBytes, kBwdNkb, p.n_tiles, tmem_base, lane);
     } else {
         // ===================== epilogue: store [dx_below | dh_prev] =====================
+        TC_PROF_DECL
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
             const int a = tcount & 1;
             const uint32_t aph = (tcount >> 1) & 1;
             const int64_t r = (int64_t)tile * kTileM + warp * 32 + lane;
             const bool valid = r < p.rows;
-            mbar_wait(&bar->tmem_full[a], aph);
+            mbar_wait(&bar->tmem_full[a], aph, 3);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * N;
 #pragma unroll 1
@@ -541,14 +577,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
             tc_fence_before();
             mbar_arrive(&bar->tmem_empty[a]);
         }
+        TC_PROF_FLUSH((N == 128 ? 5 : 8), tid == 0)
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::kTmemCols);
-    for (int i = tid; i < kGateCols; i += kBwdThreads) atomicAdd(&p.dbp[i], tail->s_db[i]);
+    for (int i = tid; i < kGateCols; i += kBwdThreads) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLoaderWarps; ++w) v += tail->s_db[w][i];
+        atomicAdd(&p.dbp[i], v);
+    }
     if (l0) {
-        for (int i = tid; i < p.c_in * kGateCols; i += kBwdThreads) atomicAdd(&p.dwx[i], tail->s_dwx[i]);
+        for (int i = tid; i < kGateCols; i += kBwdThreads) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kLoaderWarps; ++w) v += tail->s_dwx[l0 ? w : 0][i];
+            atomicAdd(&p.dwx[i], v);
+        }
         if (ds_smem)
             for (int i = tid; i < (int)p.b_inner; i += kBwdThreads) atomicAdd(&p.d_s[(int64_t)i * p.t_len + p.t], tail->s_ds[i]);
     }
@@ -567,8 +614,8 @@ constexpr int kWgRows = 32;                                        // K per stag
 constexpr int kWgABytes = 128 * kWgRows * 4;                       // 16 KB  [128 m][32 k] K-major
 constexpr int kWgBBytes = 256 * kWgRows * 4;                       // 32 KB  [256 n][32 k] K-major
 constexpr int kWgStageBytes = 2 * kWgABytes + 2 * kWgBBytes;       // 96 KB
-constexpr int kWgLoaderWarps = 8;
-constexpr int kWgThreads = (kWgLoaderWarps + 1) * 32;              // 288
+constexpr int kWgLoaderWarps = 16;
+constexpr int kWgThreads = (kWgLoaderWarps + 1) * 32;              // 544
 
 struct WgTail {
     uint64_t full[kWgStages];
@@ -630,8 +677,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
 
     if (warp < kMmaWarp) {
         // ===================== loaders: HBM rows -> tf32 hi/lo -> MN-major swizzled atoms =====================
+        TC_PROF_DECL
         const int ltid = tid;
-        struct Buf { float4 a[4]; float4 b[8]; };
+        constexpr int kNA = 1024 / kLoaders, kNB = 2048 / kLoaders, kQStep = kLoaders / 32;
+        struct Buf { float4 a[kNA]; float4 b[kNB]; };
         auto load = [&](int64_t chunk, Buf& buf) {
             const int t = (int)(chunk / p.chunks_per_t);
             const int64_t r0 = (chunk % p.chunks_per_t) * kWgRows;
@@ -639,8 +688,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
             const float* s1 = (t > 0) ? p.seg1 + (int64_t)(t - 1) * p.rows * kHid : p.h0;
             const float* dt = p.da + (int64_t)t * p.rows * kGateCols;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = ltid & 31, q = (ltid >> 5) + 8 * i;      // lane <-> row (K index), q: float4 along M
+            for (int i = 0; i < kNA; ++i) {
+                const int row = ltid & 31, q = (ltid >> 5) + kQStep * i;   // lane <-> row (K index), q: float4 along M
                 const int64_t r = r0 + row;
                 // kd = 128: m 0..63 from seg0 (h_below), 64..127 from seg1 (h_prev); kd = 64: m 0..63 from seg1
                 const float* src = (p.kd == 128) ? (q < 16 ? s0 : s1) : (q < 16 ? s1 : nullptr);
@@ -648,40 +697,48 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
                 if (src != nullptr && r < p.rows) buf.a[i] = *reinterpret_cast<const float4*>(src + r * kHid + (q & 15) * 4);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = ltid & 31, q = (ltid >> 5) + 8 * i;      // q: float4 along N (64 per row)
+            for (int i = 0; i < kNB; ++i) {
+                const int row = ltid & 31, q = (ltid >> 5) + kQStep * i;   // q: float4 along N (64 per row)
                 const int64_t r = r0 + row;
                 buf.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (r < p.rows) buf.b[i] = *reinterpret_cast<const float4*>(dt + r * kGateCols + q * 4);
             }
         };
         uint32_t it = 0;
-        int64_t chunk = blockIdx.x;
-        bool have = chunk < p.total_chunks;
-        Buf cur, nxt;
-        if (have) load(chunk, cur);
-        while (have) {
-            const int64_t nchunk = chunk + gridDim.x;
-            const bool nhave = nchunk < p.total_chunks;
-            if (nhave) load(nchunk, nxt);
+        auto process = [&](const Buf& cur) {
             const int s = it % kWgStages;
             const uint32_t ph = (it / kWgStages) & 1;
-            mbar_wait(&tail->empty[s], ph ^ 1);
+            mbar_wait(&tail->empty[s], ph ^ 1, 0);
             uint8_t* st = smem + (size_t)s * kWgStageBytes;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                split_store_t(st, st + kWgABytes, 4 * ((ltid >> 5) + 8 * i), ltid & 31, cur.a[i]);
+            for (int i = 0; i < kNA; ++i)
+                split_store_t(st, st + kWgABytes, 4 * ((ltid >> 5) + kQStep * i), ltid & 31, cur.a[i]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                split_store_t(st + 2 * kWgABytes, st + 2 * kWgABytes + kWgBBytes, 4 * ((ltid >> 5) + 8 * i), ltid & 31, cur.b[i]);
+            for (int i = 0; i < kNB; ++i)
+                split_store_t(st + 2 * kWgABytes, st + 2 * kWgABytes + kWgBBytes, 4 * ((ltid >> 5) + kQStep * i), ltid & 31, cur.b[i]);
             fence_proxy_async_smem();
             mbar_arrive(&tail->full[s]);
-            cur = nxt;
-            chunk = nchunk; have = nhave; ++it;
+            ++it;
+        };
+        int64_t chunk = blockIdx.x;
+        bool have = chunk < p.total_chunks;
+        Buf b0, b1;
+        if (have) load(chunk, b0);
+        while (have) {
+            chunk += gridDim.x;
+            have = chunk < p.total_chunks;
+            if (have) load(chunk, b1);
+            process(b0);
+            if (!have) break;
+            chunk += gridDim.x;
+            have = chunk < p.total_chunks;
+            if (have) load(chunk, b0);
+            process(b1);
         }
+        TC_PROF_FLUSH(9, ltid == 0)
         // ===================== epilogue (warps 0-3): accumulator rows = kd index -> red.add into dWp =====================
         if (warp < 4 && has_work) {
-            mbar_wait(&tail->done, 0);
+            mbar_wait(&tail->done, 0, 3);
             tc_fence_after();
             const int m = warp * 32 + lane;
             const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -699,11 +756,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
     } else {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = idesc_tf32(128, kGateCols);
+        TC_PROF_DECL
         uint32_t it = 0;
         for (int64_t chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x, ++it) {
             const int s = it % kWgStages;
             const uint32_t ph = (it / kWgStages) & 1;
-            mbar_wait(&tail->full[s], ph);
+            mbar_wait(&tail->full[s], ph, 1);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t st = smem_u32(smem + (size_t)s * kWgStageBytes);
@@ -723,6 +781,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
         }
         if (lane == 0 && has_work) mma_commit(&tail->done);
         __syncwarp();
+        TC_PROF_FLUSH(10, lane == 0)
     }
     tc_fence_before();
     __syncthreads();
@@ -876,3 +935,15 @@ extern "C" int32_t stmgcn_lstm_pack_tc(const float* wp, int32_t kd, int32_t hid,
     }
     return check_launch("lstm_pack_tc");
 }
+
+#ifdef STMGCN_TC_PROFILE
+extern "C" int32_t stmgcn_dbg_tc_prof(unsigned long long* host_out, int32_t reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_out, stmgcn::tc::g_tc_prof, sizeof(unsigned long long) * 64);
+    if (reset) {
+        unsigned long long z[64] = {0};
+        cudaMemcpyToSymbol(stmgcn::tc::g_tc_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif

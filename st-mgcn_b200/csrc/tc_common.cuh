@@ -48,11 +48,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_raw(uint64_t* bar, uint32_t parity) {
     for (uint32_t it = 0; it < (1u << 22); ++it)
         if (mbar_try_wait(bar, parity)) return;
     __trap();
 }
+// Optional wait-time accounting (built with -DSTMGCN_TC_PROFILE): cycles each role spends blocked on each barrier
+// class, summed per launch into g_tc_prof[slot]; slot = role*4 + barrier class.  Read with stmgcn_dbg_tc_prof().
+#ifdef STMGCN_TC_PROFILE
+__device__ unsigned long long g_tc_prof[64];
+struct WaitProf {
+    unsigned long long acc[4] = {0, 0, 0, 0};
+    long long t_start;
+    __device__ WaitProf() { t_start = clock64(); }
+    __device__ void flush(int role, bool leader) {
+        if (leader) {
+            for (int i = 0; i < 4; ++i) atomicAdd(&g_tc_prof[role * 4 + i], acc[i]);
+            atomicAdd(&g_tc_prof[48 + role], (unsigned long long)(clock64() - t_start));
+        }
+    }
+};
+#define TC_PROF_DECL WaitProf _wp;
+#define TC_PROF_FLUSH(role, leader) _wp.flush(role, leader);
+#define mbar_wait(bar, parity, cls) do { long long _t0 = clock64(); mbar_wait_raw(bar, parity); _wp.acc[cls] += clock64() - _t0; } while (0)
+#else
+#define TC_PROF_DECL
+#define TC_PROF_FLUSH(role, leader)
+#define mbar_wait(bar, parity, cls) mbar_wait_raw(bar, parity)
+#endif
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies read smem through it)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -25,6 +25,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
     "-Xptxas", "-v",
+] + (["-DSTMGCN_TC_PROFILE"] if os.environ.get("STMGCN_TC_PROFILE") else []) + [
 ]
 # --use_fast_math is deliberately NOT applied blindly: see below (we keep IEEE div/sqrt, only fast exp).
 NVCC_FLAGS.remove("--use_fast_math")
