@@ -125,14 +125,18 @@ int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
                              const float* wx, const float* const* wp, const float* const* bp,
                              const float* const* wimg, const float* h0, const float* c0, float* hs, float* cs,
                              float* gates, void* stream);
-/* Tensor-core operand images of one packed layer (H = 64 only).  wp (kd, 4H) -> two images, each kd*256*2
- * floats, made of 32-wide k-blocks of [hi | lo] K-major 128B-swizzled fp32 tiles holding the tf32 hi / lo split
- * of the weights (3xTF32 scheme): img_fwd = operand of gates = A . Wp (tiles [256][32]); img_bwd (may be NULL) =
- * operand of [dx | dh] = dA . Wp^T (tiles [kd][32]).  Passing wimg[l] / wimg_t[l] != NULL to
- * stmgcn_lstm_step_fwd / _bwd selects the tcgen05 kernels for that layer; NULL (or H != 64) runs the exact-FFMA
- * kernels.  Both paths read and write the same tape. */
-int32_t stmgcn_lstm_pack_tc(const float* wp, int32_t kd, int32_t hid, float* img_fwd, float* img_bwd,
-                            void* stream);
+/* Tensor-core operand images of one packed layer (H = 64 only): 32-wide k-blocks of [hi | lo] K-major
+ * 128B-swizzled fp32 tiles holding the tf32 hi / lo split of the weights (3xTF32 scheme).
+ *   img_fwd (kd_fwd*256*2 floats) from wp_fwd (kd_fwd, 4H): operand of gates = A . Wp (tiles [256][32]).
+ *           Layers > 0: wp_fwd = wp[l], kd_fwd = 128.  Layer 0: the AUGMENTED operand (96, 4H) =
+ *           [W_hh^T (64 rows) ; W_ih^T (C rows) ; b_ih + b_hh (1 row) ; zeros] -- the forward kernel feeds
+ *           [h_prev | x*s | 1 | 0] so the input term and the bias come out of the MMA.
+ *   img_bwd (kd_bwd*256*2 floats, may be NULL) from wp_bwd = wp[l] (kd_bwd = 64 or 128): operand of
+ *           [dx | dh] = dA . Wp^T (tiles [kd][32]).
+ * Passing wimg[l] / wimg_t[l] != NULL to stmgcn_lstm_step_fwd / _bwd selects the tcgen05 kernels for that layer;
+ * NULL (or H != 64) runs the exact-FFMA kernels.  Both paths read and write the same tape. */
+int32_t stmgcn_lstm_pack_tc(const float* wp_fwd, int32_t kd_fwd, const float* wp_bwd, int32_t kd_bwd, int32_t hid,
+                            float* img_fwd, float* img_bwd, void* stream);
 /* BPTT step t (call t = T-1 .. 0).  d_top: (R, H) gradient of hs[L-1][T-1] (read at t = T-1 only).
  * Workspaces, zeroed by the caller before t = T-1: dh_rec, dc: (L, R, H); dx_work: (R, H).
  * gates[l][t] is overwritten IN PLACE with the pre-activation gradients dA (stmgcn_lstm_wgrad reads them).

@@ -12,10 +12,10 @@
 using namespace stmgcn;
 
 namespace stmgcn {
-int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, const float* wimg, const float* bias,
-                            const float* wx, const float* xo, const float* sg, int c_in, int t, int t_len,
-                            int64_t b_inner, const float* c_prev, float* h_out, float* c_out, float* gates_out,
-                            int64_t rows, cudaStream_t st);
+int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int aux, const float* wimg, const float* bias,
+                            const float* xo, const float* sg, int c_in, int t, int t_len, int64_t b_inner,
+                            const float* c_prev, float* h_out, float* c_out, float* gates_out, int64_t rows,
+                            cudaStream_t st);
 int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* c_prev, const float* dh_in,
                            float* dh_rec, float* dc, float* dx_out, const float* wimg_t, float* dbp, const float* wx,
                            float* dwx, const float* xo, const float* sg, float* d_s, int c_in, int t, int t_len,
@@ -306,7 +306,7 @@ int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
                            (!epi.gates_out || aligned16(epi.gates_out)) && (!c_prev || aligned16(c_prev)) &&
                            (!a.seg[0] || aligned16(a.seg[0])) && (a.nseg < 2 || !a.seg[1] || aligned16(a.seg[1]));
         if (tc_ok) {   // tcgen05 3xTF32 path (lstm_tc.cu)
-            rc = launch_lstm_cell_tc(a.seg[0], a.nseg > 1 ? a.seg[1] : nullptr, a.nseg, wimg[l], bp[l], epi.wx, xo,
+            rc = launch_lstm_cell_tc(a.seg[0], a.nseg > 1 ? a.seg[1] : nullptr, a.nseg, l == 0 ? 1 : 0, wimg[l], bp[l], xo,
                                      s_gate, c_in, t, t_len, b_inner, c_prev, epi.h_out, epi.c_out, epi.gates_out,
                                      rows, st);
             if (rc) return rc;

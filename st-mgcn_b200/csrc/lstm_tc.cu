@@ -111,11 +111,11 @@ constexpr int kFwdN = kGateCols;
 constexpr int kFwdStages = 2;
 constexpr int kFwdBBytes = kFwdN * kKB * 4;                       // 32 KB
 constexpr int kFwdStageBytes = 2 * kABytes + 2 * kFwdBBytes;      // 96 KB
-constexpr int kFwdEpiWarps = 8;
-constexpr int kFwdLoaderWarps = 4;                                // 13 warps: 128-register budget per thread
+constexpr int kFwdEpiWarps = 16;                                  // 4 per TMEM lane quadrant: the epilogue is
+constexpr int kFwdLoaderWarps = 8;                                // latency-bound, thread-level parallelism pays
 constexpr int kFwdLoaders = kFwdLoaderWarps * 32;
-constexpr int kFwdThreads = (kFwdEpiWarps + kFwdLoaderWarps + 1) * 32;   // 416
-constexpr int kStagingBytes = 32 * 32 * 4;                        // per epilogue warp: [32 rows][32 cols] fp32
+constexpr int kFwdThreads = (kFwdEpiWarps + kFwdLoaderWarps + 1) * 32;   // 800
+constexpr int kStagingBytes = 32 * 16 * 4;                        // per epilogue warp: [32 rows][16 cols] fp32
 constexpr int kMaxC = 4;
 
 struct FwdTail {
@@ -128,10 +128,10 @@ constexpr size_t kFwdSmem = 1024 + (size_t)kFwdStages * kFwdStageBytes + (size_t
 struct CellParams {
     const float* seg0;       // (rows, 64) first K segment  (h_below for l>0, h_prev for l==0) or nullptr = zeros
     const float* seg1;       // (rows, 64) second K segment (h_prev for l>0) or nullptr
-    int nkb;                 // k-blocks: 2 per segment
+    int nkb;                 // k-blocks: 2 per segment (+1 auxiliary block for layer 0)
+    int aux;                 // layer 0: k-block 2 holds [x*s (C cols) | 1 | 0...] so that x.W_ih + b runs on the MMA
     const float* wimg;       // nkb x [hi 32 KB | lo 32 KB] pre-swizzled weight images
-    const float* bias;       // (256)
-    const float* wx;         // (C,256) layer 0 only, else nullptr
+    const float* bias;       // (256) or nullptr when folded into the auxiliary block
     const float* xo;         // (rows, T, C)
     const float* sg;         // (B, T)
     int c_in, t, t_len;
@@ -157,29 +157,47 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
 
     if (tid == 0) init_barriers(bar, kFwdStages, kFwdEpiWarps * 32, kFwdLoaders);
     if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, 512);
-    for (int i = tid; i < kGateCols; i += kFwdThreads) tail->bias[i] = p.bias[i];
+    for (int i = tid; i < kGateCols; i += kFwdThreads) tail->bias[i] = p.bias ? p.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bar->tmem_base;
 
     if (warp >= kFwdEpiWarps && warp < kMmaWarp) {
-        // ===================== loaders / tf32 splitters (register double-buffered) =====================
+        // ===================== loaders / tf32 splitters (register ping-pong) =====================
         TC_PROF_DECL
         const int ltid = tid - kFwdEpiWarps * 32;
-        const int c = ltid & 7, rsub = ltid >> 3;          // rows rsub + 16*i, 16-byte chunk c of the 128-byte row
-        auto load = [&](int tile, int kb, float4 (&buf)[8]) {
+        const int c = ltid & 7, rsub = ltid >> 3;          // rows rsub + 32*i, 16-byte chunk c of the 128-byte row
+        auto load = [&](int tile, int kb, float4 (&buf)[4]) {
+            if (p.aux && kb == 2) {                        // auxiliary block: modulated input columns and the constant 1
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t r = (int64_t)tile * kTileM + rsub + 32 * i;
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (c < 2 && r < p.rows) {
+                        const float sv = p.sg[(r % p.b_inner) * p.t_len + p.t];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int col = 4 * c + j;
+                            if (col < p.c_in) v[j] = p.xo[(r * p.t_len + p.t) * p.c_in + col] * sv;
+                            else if (col == p.c_in) v[j] = 1.0f;
+                        }
+                    }
+                    buf[i] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                return;
+            }
             const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
             const int koff = (kb & 1) * kKB + c * 4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t r = (int64_t)tile * kTileM + rsub + 16 * i;
+            for (int i = 0; i < 4; ++i) {
+                const int64_t r = (int64_t)tile * kTileM + rsub + 32 * i;
                 buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (seg != nullptr && r < p.rows) buf[i] = *reinterpret_cast<const float4*>(seg + r * kHid + koff);
             }
         };
         uint32_t it = 0;
-        auto process = [&](const float4 (&cur)[8], int kb) {
+        auto process = [&](const float4 (&cur)[4], int kb) {
             const int s = it % kFwdStages;
             const uint32_t ph = (it / kFwdStages) & 1;
             mbar_wait(&bar->empty[s], ph ^ 1, 0);
@@ -191,8 +209,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                 bulk_g2s(st + 2 * kABytes + kFwdBBytes, src + kFwdBBytes / 4, kFwdBBytes, &bar->full[s]);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = rsub + 16 * i;
+            for (int i = 0; i < 4; ++i) {
+                const int row = rsub + 32 * i;
                 split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), cur[i]);
             }
             fence_proxy_async_smem();
@@ -202,7 +220,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
         // ping-pong between two register buffers (no copies: a copy would wait for the prefetch it is hiding)
         int tile = blockIdx.x, kb = 0;
         bool have = tile < p.n_tiles;
-        float4 b0[8], b1[8];
+        float4 b0[4], b1[4];
         if (have) load(tile, kb, b0);
         while (have) {
             int ck = kb;
@@ -221,9 +239,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
     } else if (warp == kMmaWarp) {
         mma_issuer<kFwdN, kFwdStages, 0>(bar, smem, kFwdStageBytes, kFwdBBytes, p.nkb, p.n_tiles, tmem_base, lane);
     } else {
-        // ===================== epilogue: LSTM cell (8 warps: TMEM lane quadrant q, column half hsel) ============
+        // ===================== epilogue: LSTM cell =====================
+        // 16 warps: TMEM lane quadrant q = warp & 3 (rows 32q..32q+31 of the tile), column quarter part = warp >> 2
+        // (units 16*part .. 16*part+15), processed as four 16-column pieces of 4 units each.
         TC_PROF_DECL
-        const int q = warp & 3, hsel = warp >> 2;
+        const int q = warp & 3, part = warp >> 2;
         float* stg = reinterpret_cast<float*>(staging + (size_t)warp * kStagingBytes);
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
@@ -232,57 +252,32 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
             const int64_t r0 = (int64_t)tile * kTileM + q * 32;     // first row of this warp
             const int64_t r = r0 + lane;
             const bool valid = r < p.rows;
-            float xs[kMaxC];
-#pragma unroll
-            for (int c = 0; c < kMaxC; ++c) xs[c] = 0.f;
-            if (p.wx != nullptr && valid) {
-                const float sv = p.sg[(r % p.b_inner) * p.t_len + p.t];
-#pragma unroll
-                for (int c = 0; c < kMaxC; ++c)
-                    if (c < p.c_in) xs[c] = p.xo[(r * p.t_len + p.t) * p.c_in + c] * sv;
-            }
-            float4 cpv[4];                                  // c_{t-1} for two chunks, prefetched two chunks ahead
+            float4 cpv[4];                                          // this warp's 16 units of c_{t-1}
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 cpv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.c_prev != nullptr && valid)
-                    cpv[j] = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + hsel * 32 + 4 * j);
+                    cpv[j] = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + part * 16 + 4 * j);
             }
             mbar_wait(&bar->tmem_full[a], aph, 3);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * kFwdN;
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * kFwdN + (uint32_t)part * 64;
 #pragma unroll
-            for (int ci = 0; ci < 4; ++ci) {
-                const int chunk = hsel * 4 + ci;                 // 32 gate columns = units [8*chunk, 8*chunk+8)
-                uint32_t v[32];
-                tmem_ld32(t_row + chunk * 32, v);
-                const float4 cpa = cpv[2 * (ci & 1)], cpb = cpv[2 * (ci & 1) + 1];
-                const float cp[8] = {cpa.x, cpa.y, cpa.z, cpa.w, cpb.x, cpb.y, cpb.z, cpb.w};
-                if (ci < 2 && p.c_prev != nullptr && valid) {
-                    cpv[2 * (ci & 1)] = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + (chunk + 2) * 8);
-                    cpv[2 * (ci & 1) + 1] = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + (chunk + 2) * 8 + 4);
-                }
+            for (int pc = 0; pc < 4; ++pc) {                        // piece: 16 gate columns = 4 units
+                uint32_t v[16];
+                tmem_ld16(t_row + pc * 16, v);
+                const int unit0 = part * 16 + pc * 4;
+                const float cp[4] = {cpv[pc].x, cpv[pc].y, cpv[pc].z, cpv[pc].w};
                 tmem_ld_wait();
-                float hn[8], cn[8];
+                float hn[4], cn[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int col = chunk * 32 + 4 * u;
-                    float pi = __uint_as_float(v[4 * u + 0]) + tail->bias[col + 0];
-                    float pf = __uint_as_float(v[4 * u + 1]) + tail->bias[col + 1];
-                    float pg = __uint_as_float(v[4 * u + 2]) + tail->bias[col + 2];
-                    float po = __uint_as_float(v[4 * u + 3]) + tail->bias[col + 3];
-                    if (p.wx != nullptr) {
-#pragma unroll
-                        for (int c = 0; c < kMaxC; ++c) {
-                            if (c < p.c_in) {
-                                const float4 wv = __ldg(reinterpret_cast<const float4*>(p.wx + c * kGateCols + col));
-                                pi = fmaf(xs[c], wv.x, pi);
-                                pf = fmaf(xs[c], wv.y, pf);
-                                pg = fmaf(xs[c], wv.z, pg);
-                                po = fmaf(xs[c], wv.w, po);
-                            }
-                        }
-                    }
+                for (int u = 0; u < 4; ++u) {
+                    const int col = 4 * (unit0 + u);
+                    const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[col]);
+                    const float pi = __uint_as_float(v[4 * u + 0]) + bv.x;
+                    const float pf = __uint_as_float(v[4 * u + 1]) + bv.y;
+                    const float pg = __uint_as_float(v[4 * u + 2]) + bv.z;
+                    const float po = __uint_as_float(v[4 * u + 3]) + bv.w;
                     const float gi = sigmoidf_(pi), gf = sigmoidf_(pf), gg = tanhf_(pg), go = sigmoidf_(po);
                     cn[u] = fmaf(gf, cp[u], gi * gg);
                     hn[u] = go * tanhf_(cn[u]);
@@ -292,28 +287,24 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                     v[4 * u + 3] = __float_as_uint(go);
                 }
                 if (valid) {
-                    float* hd = p.h_out + r * kHid + chunk * 8;
-                    float* cd = p.c_out + r * kHid + chunk * 8;
-                    *reinterpret_cast<float4*>(hd) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    *reinterpret_cast<float4*>(hd + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-                    *reinterpret_cast<float4*>(cd) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                    *reinterpret_cast<float4*>(cd + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                    *reinterpret_cast<float4*>(p.h_out + r * kHid + unit0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                    *reinterpret_cast<float4*>(p.c_out + r * kHid + unit0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                 }
                 if (p.gates_out != nullptr) {
-                    // gate tape: transpose through this warp's staging tile so every store instruction writes
-                    // 4 full 128-byte row segments instead of 32 scattered 16-byte pieces
+                    // gate tape: transpose through this warp's [32][16] staging tile so a store instruction writes
+                    // 8 row segments of 64 contiguous bytes instead of 32 scattered 16-byte pieces
                     __syncwarp();
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        *reinterpret_cast<uint4*>(stg + lane * 32 + ((u ^ (lane & 7)) << 2)) =
+                    for (int u = 0; u < 4; ++u)
+                        *reinterpret_cast<uint4*>(stg + lane * 16 + ((u ^ ((lane >> 1) & 3)) << 2)) =
                             make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
                     __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = i * 4 + (lane >> 3), qq = lane & 7;
-                        const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 32 + ((qq ^ (row & 7)) << 2));
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = i * 8 + (lane >> 2), qq = lane & 3;
+                        const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 16 + ((qq ^ ((row >> 1) & 3)) << 2));
                         if (r0 + row < p.rows)
-                            *reinterpret_cast<uint4*>(p.gates_out + (r0 + row) * kGateCols + chunk * 32 + qq * 4) = val;
+                            *reinterpret_cast<uint4*>(p.gates_out + (r0 + row) * kGateCols + 4 * unit0 + qq * 4) = val;
                     }
                 }
             }
@@ -812,11 +803,12 @@ __global__ void pack_image_kernel(const float* __restrict__ src, int n_rows, int
 
 namespace stmgcn {
 
-// Called from stmgcn_lstm_step_fwd (lstm.cu) when the tensor-core path applies.
-int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, const float* wimg, const float* bias,
-                            const float* wx, const float* xo, const float* sg, int c_in, int t, int t_len,
-                            int64_t b_inner, const float* c_prev, float* h_out, float* c_out, float* gates_out,
-                            int64_t rows, cudaStream_t st) {
+// Called from stmgcn_lstm_step_fwd (lstm.cu) when the tensor-core path applies.  aux != 0 (layer 0): the weight image
+// carries a third k-block [W_ih^T ; b ; 0] and the loader feeds [x*s | 1 | 0] so x.W_ih + b comes out of the MMA.
+int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int aux, const float* wimg, const float* bias,
+                            const float* xo, const float* sg, int c_in, int t, int t_len, int64_t b_inner,
+                            const float* c_prev, float* h_out, float* c_out, float* gates_out, int64_t rows,
+                            cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         STMGCN_CUDA(cudaFuncSetAttribute(lstm_cell_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
@@ -825,10 +817,10 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, cons
     CellParams p;
     p.seg0 = seg0;
     p.seg1 = seg1;
-    p.nkb = 2 * nseg;
+    p.nkb = 2 * nseg + (aux ? 1 : 0);
+    p.aux = aux;
     p.wimg = wimg;
-    p.bias = bias;
-    p.wx = wx;
+    p.bias = aux ? nullptr : bias;
     p.xo = xo;
     p.sg = sg;
     p.c_in = c_in;
@@ -919,18 +911,18 @@ int32_t launch_lstm_wgrad_tc(const float* seg0, const float* seg1, const float* 
 
 }  // namespace stmgcn
 
-extern "C" int32_t stmgcn_lstm_pack_tc(const float* wp, int32_t kd, int32_t hid, float* img_fwd, float* img_bwd,
-                                       void* stream) {
-    STMGCN_REQUIRE(wp && img_fwd, STMGCN_ERR_ARG, "lstm_pack_tc: null pointer");
-    STMGCN_REQUIRE(hid == kHid && kd > 0 && kd % kKB == 0, STMGCN_ERR_SHAPE,
-                   "lstm_pack_tc: tensor-core path needs hid == 64 and kd %% 32 == 0 (got hid=%d kd=%d)", hid, kd);
-    const int total = kd * kGateCols;
+extern "C" int32_t stmgcn_lstm_pack_tc(const float* wp_fwd, int32_t kd_fwd, const float* wp_bwd, int32_t kd_bwd,
+                                       int32_t hid, float* img_fwd, float* img_bwd, void* stream) {
+    STMGCN_REQUIRE(wp_fwd && img_fwd, STMGCN_ERR_ARG, "lstm_pack_tc: null pointer");
+    STMGCN_REQUIRE(hid == kHid && kd_fwd > 0 && kd_fwd % kKB == 0, STMGCN_ERR_SHAPE,
+                   "lstm_pack_tc: tensor-core path needs hid == 64 and kd %% 32 == 0 (got hid=%d kd=%d)", hid, kd_fwd);
     cudaStream_t st = (cudaStream_t)stream;
-    // forward operand B[n = gate col][k = kd index] = wp[k][n]
-    pack_image_kernel<<<(total + 255) / 256, 256, 0, st>>>(wp, kGateCols, kd, 1, kGateCols, img_fwd);
+    // forward operand B[n = gate col][k = kd index] = wp_fwd[k][n]
+    pack_image_kernel<<<(kd_fwd * kGateCols + 255) / 256, 256, 0, st>>>(wp_fwd, kGateCols, kd_fwd, 1, kGateCols, img_fwd);
     count_launch();
-    if (img_bwd != nullptr) {   // backward operand B[n = kd index][k = gate col] = wp[n][k]
-        pack_image_kernel<<<(total + 255) / 256, 256, 0, st>>>(wp, kd, kGateCols, kGateCols, 1, img_bwd);
+    if (img_bwd != nullptr) {   // backward operand B[n = kd index][k = gate col] = wp_bwd[n][k]
+        STMGCN_REQUIRE(wp_bwd && (kd_bwd == 64 || kd_bwd == 128), STMGCN_ERR_SHAPE, "lstm_pack_tc: kd_bwd=%d", kd_bwd);
+        pack_image_kernel<<<(kd_bwd * kGateCols + 255) / 256, 256, 0, st>>>(wp_bwd, kd_bwd, kGateCols, kGateCols, 1, img_bwd);
         count_launch();
     }
     return check_launch("lstm_pack_tc");

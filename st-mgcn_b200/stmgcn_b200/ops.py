@@ -312,11 +312,18 @@ class SharedLSTM(torch.autograd.Function):
         st = _stream()
         wimg, wimg_t, wimg_arr = None, None, None
         if hid == 64 and lstm_path() == "tc":           # tcgen05 3xTF32 path: pre-swizzled hi/lo weight images
-            wimg = [torch.empty(w.shape[0] * 4 * hid * 2, device=dev, dtype=torch.float32) for w in wp]
-            wimg_t = [torch.empty_like(v) for v in wimg] if need_grad else [None] * len(wimg)
-            for w, img, img_t in zip(wp, wimg, wimg_t):
-                _lib.check(L.stmgcn_lstm_pack_tc(w.data_ptr(), w.shape[0], hid, img.data_ptr(), _p(img_t), st),
-                           "lstm_pack_tc")
+            # layer 0 forward operand is augmented: [W_hh^T ; W_ih^T ; bias ; 0] (96 rows) -- x.W_ih + b runs on the MMA
+            aug = torch.zeros((96, 4 * hid), device=dev, dtype=torch.float32)
+            aug[:hid] = wp[0]
+            aug[hid:hid + c_in] = wx
+            aug[hid + c_in] = bp[0]
+            wfwd = [aug] + list(wp[1:])
+            wimg = [torch.empty(w.shape[0] * 4 * hid * 2, device=dev, dtype=torch.float32) for w in wfwd]
+            wimg_t = [torch.empty(w.shape[0] * 4 * hid * 2, device=dev, dtype=torch.float32) if need_grad else None
+                      for w in wp]
+            for wf, wb, img, img_t in zip(wfwd, wp, wimg, wimg_t):
+                _lib.check(L.stmgcn_lstm_pack_tc(wf.data_ptr(), wf.shape[0], wb.data_ptr(), wb.shape[0], hid,
+                                                 img.data_ptr(), _p(img_t), st), "lstm_pack_tc")
             wimg_arr = _lib.ptr_array([v.data_ptr() for v in wimg])
         for t in range(t_len):
             _lib.check(L.stmgcn_lstm_step_fwd(t, t_len, n_layers, rows, hid, c_in, b, xo.data_ptr(),

@@ -253,3 +253,48 @@ def test_lstm_tensor_core_backward_matches_exact_fp32_path(rows_n, b, t, c):
     names = ["d_s"] + [f"w{i}" for i in range(4 * lyr)]
     for name, a, b_ in zip(names, res["tc"], res["fma"]):
         assert_close(a.cpu().numpy(), b_.cpu().numpy(), f"tc vs fma {name}", 5e-5)
+
+
+def test_training_loop_like_model_trainer(tmp_path):
+    """Drive the drop-in model the way Model_Trainer.py does (Adam with L2 weight decay :13, train/eval modes,
+    set_grad_enabled :33, keyword forward :35, checkpoint save/load :52,:70-71) and compare the parameter
+    trajectory with the dense CPU oracle trained identically."""
+    meta = dict(n=48, m=2, k=2, t=5, b=6, c=1, hid=64, layers=3, gcn_hid=64)
+    sups, params, x, y = _mid_case(seed=11, **meta)
+    model = build_model(meta, DEV)
+    model.load_state_dict(params)
+    opt = torch.optim.Adam(params=model.parameters(), lr=2e-3, weight_decay=1e-4)       # Main.py:13, Model_Trainer.py:13
+    crit = nn.MSELoss(reduction="mean")
+    ref = {k_: v.clone().requires_grad_(True) for k_, v in params.items()}
+    ref_opt = torch.optim.Adam(params=list(ref.values()), lr=2e-3, weight_decay=1e-4)
+    sd = [s.to(DEV) for s in sups]
+    xd, yd = x.to(DEV), y.to(DEV)
+    for step in range(3):
+        model.train()
+        with torch.set_grad_enabled(True):
+            loss = crit(model(obs_seq=xd, sta_adj_list=sd), yd)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        ref_loss = crit(O.dense_st_mgcn(ref, x, sups), y)
+        ref_opt.zero_grad()
+        ref_loss.backward()
+        ref_opt.step()
+        assert abs(loss.item() - ref_loss.item()) <= 2e-5 * max(1.0, abs(ref_loss.item())), step
+    for key, p in model.named_parameters():
+        assert_close(p.detach().cpu().numpy(), ref[key].detach().numpy(), f"param after 3 Adam steps: {key}", 2e-4)
+    # validate / test phase: eval mode, no grad, checkpoint round trip
+    model.eval()
+    with torch.set_grad_enabled(False):
+        out_eval = model(obs_seq=xd, sta_adj_list=sd)
+    path = tmp_path / "ST_MGCN_best_model.pkl"
+    torch.save({"epoch": 1, "state_dict": model.state_dict()}, path)
+    model2 = build_model(meta, DEV)
+    model2.load_state_dict(torch.load(path)["state_dict"])
+    model2.eval()
+    with torch.no_grad():
+        out2 = model2(obs_seq=xd, sta_adj_list=sd)
+    # (not bit-identical: the region pooling accumulates with atomics in a run-dependent order)
+    assert_close(out2.cpu().numpy(), out_eval.cpu().numpy(), "checkpoint round trip", 1e-5)
+    assert_close(out_eval.cpu().numpy(), O.dense_st_mgcn({k_: v.detach() for k_, v in ref.items()}, x, sups).numpy(),
+                 "eval forward after training", 2e-4)
