@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="replay the step from a captured CUDA graph (stmgcn_b200.graphs.GraphedStep); measured gain "
+                         "at cfg3 is ~1 %% -- the step is GPU-bound, not launch-bound -- so eager is the default")
     return ap.parse_args()
 
 
@@ -179,7 +182,8 @@ def workload_config(w, world, per_gpu_batch):
                         f"L={w.lstm_layers} G={w.gcn_hidden} C={w.input_dim}, graph density {w.density}",
             "global_batch": per_gpu_batch * world, "parallelism": f"dp{world}",
             "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
-            "step": "forward + MSELoss + backward (+ one gradient all-reduce when world > 1); optimizer excluded"}
+            "step": "forward + MSELoss + backward (+ one gradient all-reduce when world > 1); optimizer excluded",
+            "cuda_graph": None}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -191,7 +195,7 @@ def run_ours(args, w):
     from torch import nn
     import GCN
     import STMGCN
-    from stmgcn_b200 import _lib, dp, ops, synth
+    from stmgcn_b200 import _lib, dp, graphs, ops, synth
     from stmgcn_b200.graph import supports_from_dense
 
     rank, world, local_rank = dp.init_from_env()
@@ -212,13 +216,29 @@ def run_ours(args, w):
     x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
     x_d, y_d = x_h.to(dev), y_h.to(dev)
 
-    def step(x, y):
+    use_graph = args.cuda_graph
+    launches_per_step = None
+    if use_graph:
+        # one eager step to count this library's launches, then capture fwd + loss + bwd (+ all-reduce) once
+        l0 = _lib.launch_count()
         bucket.zero_()
-        out = model(obs_seq=x, sta_adj_list=sups)
-        loss = crit(out, y)
-        loss.backward()
-        bucket.all_reduce_mean_()
-        return loss
+        crit(model(obs_seq=x_d, sta_adj_list=sups), y_d).backward()
+        torch.cuda.synchronize()
+        launches_per_step = _lib.launch_count() - l0
+        gstep = graphs.GraphedStep(model, crit, x_d, y_d, sups, bucket=bucket, all_reduce=False)
+
+        def step(x, y):
+            loss = gstep(x, y)
+            bucket.all_reduce_mean_()          # the one collective of the step stays outside the graph (NCCL, eager)
+            return loss
+    else:
+        def step(x, y):
+            bucket.zero_()
+            out = model(obs_seq=x, sta_adj_list=sups)
+            loss = crit(out, y)
+            loss.backward()
+            bucket.all_reduce_mean_()
+            return loss
 
     def barrier():
         if world > 1:
@@ -246,7 +266,7 @@ def run_ours(args, w):
         sampler.start()
     l0 = _lib.launch_count()
     ms_total = timed(lambda: step(x_d, y_d), args.steps)
-    launches = (_lib.launch_count() - l0) // args.steps
+    launches = (_lib.launch_count() - l0) // args.steps if launches_per_step is None else launches_per_step
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     units = b * world * w.n_regions * w.seq_len
@@ -258,9 +278,12 @@ def run_ours(args, w):
         x_buf, y_buf = torch.empty_like(x_d), torch.empty_like(y_d)
 
         def e2e_step():
-            x_buf.copy_(x_h, non_blocking=True)
-            y_buf.copy_(y_h, non_blocking=True)
-            loss = step(x_buf, y_buf)
+            if use_graph:                                       # pinned host -> the graph's static input buffers
+                loss = step(x_h, y_h)
+            else:
+                x_buf.copy_(x_h, non_blocking=True)
+                y_buf.copy_(y_h, non_blocking=True)
+                loss = step(x_buf, y_buf)
             return loss.item()                                  # device -> host read of the step's result
 
         for _ in range(2):
@@ -321,7 +344,8 @@ def run_ours(args, w):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(w, world, b), "clocks": clocks, "gpu_launches": int(launches),
+                "config": dict(workload_config(w, world, b), cuda_graph=use_graph), "clocks": clocks,
+                "gpu_launches": int(launches),
                 "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:
