@@ -88,7 +88,12 @@ int32_t stmgcn_obs_to_node_major(const float* obs, float* xo, float* xt, int64_t
  * S_0[r,j] + out[r,j]  (caller zeroes pool; sum over regions of x_hat, not yet divided by N). */
 int32_t stmgcn_proj_fwd(const float* s, int64_t stride_k, int32_t ks, int64_t rows, int32_t p,
                         const float* w, const float* bias, int32_t q, int32_t act, float* out,
-                        float* pool, int64_t b_inner, void* stream);
+                        float* pool, int64_t b_inner, const float* wimg, void* stream);
+/* Tensor-core operand images of W (ks*64, 64) for p = q = 64, ks <= 4 (3xTF32, see stmgcn_lstm_pack_tc):
+ * img_fwd: ks*64*64*2 floats; img_bwd (may be NULL): 2*2*256*32 floats, ZERO-FILLED by the caller (rows beyond
+ * ks*64 stay zero).  Passing wimg / wimg_t != NULL to stmgcn_proj_fwd / _bwd selects the tcgen05 kernels when
+ * p = q = 64 (and, for the backward, a full d_out and u are given); otherwise the exact-FFMA kernels run. */
+int32_t stmgcn_proj_pack_tc(const float* w, int32_t ks, float* img_fwd, float* img_bwd, void* stream);
 /* backward of the projection.  dZ = dOut (.) [out > 0] (act = RELU) with dOut either a full (rows, q)
  * tensor (d_out) or, when d_out_bcast != NULL, the broadcast dOut[r,:] = d_out_bcast[(r % b_inner), :] *
  * bcast_scale (the mean-pool adjoint dz/N, STMGCN.py:42).  dz_work: (rows, q) workspace receiving dZ.
@@ -97,7 +102,8 @@ int32_t stmgcn_proj_fwd(const float* s, int64_t stride_k, int32_t ks, int64_t ro
 int32_t stmgcn_proj_bwd(const float* s, int64_t stride_k, int32_t ks, int64_t rows, int32_t p,
                         const float* wt, int32_t q, int32_t act, const float* out, const float* d_out,
                         const float* d_out_bcast, float bcast_scale, int64_t b_inner, float* dz_work,
-                        float* dw, float* dbias, float* u, int64_t stride_u, void* stream);
+                        float* dw, float* dbias, float* u, int64_t stride_u, const float* wimg_t,
+                        void* stream);
 
 /* ---- K3a: context gate (STMGCN.py:42-43) -----------------------------------------------------------
  * z = pool / n_regions; a1 = z fcw^T + fcb; s = sigmoid(relu(a1) fcw^T + fcb).  All (B, T); fcw (T,T). */

@@ -15,94 +15,15 @@
 //   MMA warp       : one thread issues tcgen05.mma kind::tf32, 12 per 32-wide k-block (3 passes x 4 k-slices);
 //                    tcgen05.commit releases operand stages / publishes accumulators
 // Pipelines: operand stages (full/empty mbarriers) and two TMEM accumulators (tmem_full/tmem_empty).
-#include "tc_common.cuh"
+#include "tc_pipeline.cuh"
 
 using namespace stmgcn;
 using namespace stmgcn::tc;
 
 namespace {
 
-constexpr int kTileM = 128;
-constexpr int kKB = 32;              // k-block: one 128-byte swizzle row of fp32
-constexpr int kHid = 64;
-constexpr int kGateCols = 256;       // 4H
-constexpr int kMaxStages = 3;
-constexpr int kAccs = 2;
-constexpr int kABytes = kTileM * kKB * 4;            // 16 KB per hi or lo A tile
 constexpr int kNumLoaders = 512;     // 16 loader warps (backward): the loaders are latency-bound, TLP is what helps
 constexpr int kLoaderWarps = kNumLoaders / 32;
-
-struct Barriers {
-    uint64_t full[kMaxStages];
-    uint64_t empty[kMaxStages];
-    uint64_t tmem_full[kAccs];
-    uint64_t tmem_empty[kAccs];
-    uint32_t tmem_base;
-};
-
-__device__ __forceinline__ void init_barriers(Barriers* b, int stages, int n_epi_threads, int n_loaders) {
-    for (int s = 0; s < stages; ++s) {
-        mbar_init(&b->full[s], n_loaders + 1);
-        mbar_init(&b->empty[s], 1);
-    }
-    for (int a = 0; a < kAccs; ++a) {
-        mbar_init(&b->tmem_full[a], 1);
-        mbar_init(&b->tmem_empty[a], n_epi_threads);
-    }
-    fence_barrier_init();
-}
-
-// The MMA warp: for every tile, for every k-block: wait operands, issue 3 x 4 MMAs, release the stage.
-template <int N, int STAGES, int PROF_KERNEL>
-__device__ __forceinline__ void mma_issuer(Barriers* bar, uint8_t* smem, int stage_bytes, int b_bytes, int nkb,
-                                           int n_tiles, uint32_t tmem_base, int lane) {
-    constexpr uint32_t idesc = idesc_tf32(kTileM, N);
-    TC_PROF_DECL
-    uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-        const int a = tcount & 1;
-        const uint32_t aph = (tcount >> 1) & 1;
-        mbar_wait(&bar->tmem_empty[a], aph ^ 1, 2);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)a * N;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&bar->full[s], ph, 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t a_hi = smem_desc_k_sw128(st);
-                const uint64_t a_lo = smem_desc_k_sw128(st + kABytes);
-                const uint64_t b_hi = smem_desc_k_sw128(st + 2 * kABytes);
-                const uint64_t b_lo = smem_desc_k_sw128(st + 2 * kABytes + b_bytes);
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint64_t da = (pass == 1) ? a_lo : a_hi;
-                    const uint64_t db = (pass == 2) ? b_lo : b_hi;
-#pragma unroll
-                    for (int k = 0; k < kKB / 8; ++k) {
-                        const uint32_t acc = (kb > 0 || pass > 0 || k > 0) ? 1u : 0u;
-                        mma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc);
-                    }
-                }
-                mma_commit(&bar->empty[s]);
-            }
-            __syncwarp();
-        }
-        if (lane == 0) mma_commit(&bar->tmem_full[a]);
-        __syncwarp();
-    }
-    TC_PROF_FLUSH(PROF_KERNEL * 3 + 1, lane == 0)
-}
-
-__device__ __forceinline__ void split_store(uint8_t* st, uint32_t off, const float4& v) {
-    float4 hi, lo;
-    hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
-    lo.x = tf32_lo(v.x, hi.x); lo.y = tf32_lo(v.y, hi.y); lo.z = tf32_lo(v.z, hi.z); lo.w = tf32_lo(v.w, hi.w);
-    *reinterpret_cast<float4*>(st + off) = hi;
-    *reinterpret_cast<float4*>(st + kABytes + off) = lo;
-}
 
 // =====================================================================================================
 // forward cell
@@ -603,8 +524,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
 constexpr int kWgStages = 2;
 constexpr int kWgRows = 32;                                        // K per stage
 constexpr int kWgABytes = 128 * kWgRows * 4;                       // 16 KB  [128 m][32 k] K-major
-constexpr int kWgBBytes = 256 * kWgRows * 4;                       // 32 KB  [256 n][32 k] K-major
-constexpr int kWgStageBytes = 2 * kWgABytes + 2 * kWgBBytes;       // 96 KB
+template <int N> struct WgCfg {
+    static constexpr int kBBytes = N * kWgRows * 4;                // [N][32 k] K-major
+    static constexpr int kStageBytes = 2 * kWgABytes + 2 * kBBytes;
+    static constexpr size_t kSmem = 1024 + (size_t)kWgStages * kStageBytes + 64;
+    static constexpr int kTmemCols = N < 32 ? 32 : N;
+};
 constexpr int kWgLoaderWarps = 16;
 constexpr int kWgThreads = (kWgLoaderWarps + 1) * 32;              // 544
 
@@ -614,14 +539,15 @@ struct WgTail {
     uint64_t done;
     uint32_t tmem_base;
 };
-constexpr size_t kWgSmem = 1024 + (size_t)kWgStages * kWgStageBytes + sizeof(WgTail);
+static_assert(sizeof(WgTail) <= 64, "WgTail");
 
 struct WgParams {
     const float* seg0;       // h_below tape base for this layer: (T, rows, 64) or nullptr (layer 0)
     const float* seg1;       // this layer's h tape base (T, rows, 64): read shifted by one step
     const float* h0;         // (rows, 64) value of h_{-1} or nullptr (zeros)
-    const float* da;         // (T, rows, 256)
-    float* dwp;              // (kd, 256) +=
+    const float* da;         // (T, rows, N)
+    float* dwp;              // (kd, N) +=
+    int shift1;              // 1: seg1 is read one step back (LSTM h_{t-1}); 0: same step (projection)
     int kd;                  // 128 or 64 (layer 0: only seg1)
     int t_len;
     int64_t rows;
@@ -629,19 +555,11 @@ struct WgParams {
     int64_t total_chunks;
 };
 
-// transpose-store one float4 (4 consecutive M/N indices mn..mn+3 of row k) into a K-major swizzled tile pair
-__device__ __forceinline__ void split_store_t(uint8_t* hi_tile, uint8_t* lo_tile, int mn, int k, const float4& v) {
-    const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t off = sw128_offset((uint32_t)(mn + j), (uint32_t)k);
-        const float hi = tf32_hi(vv[j]);
-        *reinterpret_cast<float*>(hi_tile + off) = hi;
-        *reinterpret_cast<float*>(lo_tile + off) = tf32_lo(vv[j], hi);
-    }
-}
-
+template <int N>
 __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+    using Cfg = WgCfg<N>;
+    constexpr int kWgBBytes = Cfg::kBBytes;
+    constexpr int kWgStageBytes = Cfg::kStageBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     WgTail* tail = (WgTail*)(smem + (size_t)kWgStages * kWgStageBytes);
@@ -659,7 +577,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
         mbar_init(&tail->done, 1);
         fence_barrier_init();
     }
-    if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, 256);
+    if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, Cfg::kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -670,14 +588,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
         // ===================== loaders: HBM rows -> tf32 hi/lo -> MN-major swizzled atoms =====================
         TC_PROF_DECL
         const int ltid = tid;
-        constexpr int kNA = 1024 / kLoaders, kNB = 2048 / kLoaders, kQStep = kLoaders / 32;
+        constexpr int kNA = 1024 / kLoaders, kNB = (32 * N / 4) / kLoaders, kQStep = kLoaders / 32;
+        static_assert(kNB >= 1, "loader mapping");
         struct Buf { float4 a[kNA]; float4 b[kNB]; };
         auto load = [&](int64_t chunk, Buf& buf) {
             const int t = (int)(chunk / p.chunks_per_t);
             const int64_t r0 = (chunk % p.chunks_per_t) * kWgRows;
             const float* s0 = p.seg0 ? p.seg0 + (int64_t)t * p.rows * kHid : nullptr;
-            const float* s1 = (t > 0) ? p.seg1 + (int64_t)(t - 1) * p.rows * kHid : p.h0;
-            const float* dt = p.da + (int64_t)t * p.rows * kGateCols;
+            const float* s1 = p.shift1 ? ((t > 0) ? p.seg1 + (int64_t)(t - 1) * p.rows * kHid : p.h0)
+                                        : p.seg1 + (int64_t)t * p.rows * kHid;
+            const float* dt = p.da + (int64_t)t * p.rows * N;
 #pragma unroll
             for (int i = 0; i < kNA; ++i) {
                 const int row = ltid & 31, q = (ltid >> 5) + kQStep * i;   // lane <-> row (K index), q: float4 along M
@@ -692,7 +612,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
                 const int row = ltid & 31, q = (ltid >> 5) + kQStep * i;   // q: float4 along N (64 per row)
                 const int64_t r = r0 + row;
                 buf.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < p.rows) buf.b[i] = *reinterpret_cast<const float4*>(dt + r * kGateCols + q * 4);
+                if (r < p.rows) buf.b[i] = *reinterpret_cast<const float4*>(dt + r * N + q * 4);
             }
         };
         uint32_t it = 0;
@@ -734,19 +654,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
             const int m = warp * 32 + lane;
             const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-            for (int chunk32 = 0; chunk32 < kGateCols / 32; ++chunk32) {
+            for (int chunk32 = 0; chunk32 < N / 32; ++chunk32) {
                 uint32_t v[32];
                 tmem_ld32(t_row + chunk32 * 32, v);
                 tmem_ld_wait();
                 if (m < p.kd) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(p.dwp + (int64_t)m * kGateCols + chunk32 * 32 + j, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j) atomicAdd(p.dwp + (int64_t)m * N + chunk32 * 32 + j, __uint_as_float(v[j]));
                 }
             }
         }
     } else {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = idesc_tf32(128, kGateCols);
+        constexpr uint32_t idesc = idesc_tf32(128, N);
         TC_PROF_DECL
         uint32_t it = 0;
         for (int64_t chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x, ++it) {
@@ -777,26 +697,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 256);
-}
-
-// Generic K-major hi/lo image of a logical B[n][k] = src[n*rs + k*cs]: per 32-wide k-block [hi | lo], each an
-// [n_rows][32] fp32 tile with the 128-byte swizzle.
-__global__ void pack_image_kernel(const float* __restrict__ src, int n_rows, int k_cols, int64_t rs, int64_t cs,
-                                  float* __restrict__ img) {
-    const int total = n_rows * k_cols;
-    const int tile_floats = n_rows * kKB;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int n = e / k_cols, k = e % k_cols;
-        const float v = src[(int64_t)n * rs + (int64_t)k * cs];
-        const float hi = tf32_hi(v);
-        const float lo = tf32_lo(v, hi);
-        const int kb = k / kKB, kk = k % kKB;
-        const uint32_t off = sw128_offset((uint32_t)n, (uint32_t)kk) / 4;
-        float* base = img + (size_t)kb * (2 * tile_floats);
-        base[off] = hi;
-        base[tile_floats + off] = lo;
-    }
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
 }  // namespace
@@ -884,12 +785,16 @@ int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* 
 
 int lstm_tc_max_c_bwd() { return kBwdMaxC; }
 
-// Called from stmgcn_lstm_wgrad (lstm.cu).
-int32_t launch_lstm_wgrad_tc(const float* seg0, const float* seg1, const float* h0, const float* da, float* dwp, int kd,
-                             int t_len, int64_t rows, cudaStream_t st) {
+// Weight-gradient reduction on the tensor cores.  LSTM (n = 256, shift1 = 1): called from stmgcn_lstm_wgrad;
+// projection (n = 64, shift1 = 0, t_len = 1): called from stmgcn_proj_bwd, once per 128-row block of dW.
+int32_t launch_wgrad_tc(const float* seg0, const float* seg1, const float* h0, int shift1, const float* da, int n,
+                        float* dwp, int kd, int t_len, int64_t rows, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        STMGCN_CUDA(cudaFuncSetAttribute(lstm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)WgCfg<256>::kSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)WgCfg<64>::kSmem));
         attr_done = true;
     }
     WgParams p;
@@ -898,15 +803,23 @@ int32_t launch_lstm_wgrad_tc(const float* seg0, const float* seg1, const float* 
     p.h0 = h0;
     p.da = da;
     p.dwp = dwp;
+    p.shift1 = shift1;
     p.kd = kd;
     p.t_len = t_len;
     p.rows = rows;
     p.chunks_per_t = ceil_div(rows, kWgRows);
     p.total_chunks = p.chunks_per_t * t_len;
     const int64_t grid = p.total_chunks < sm_count() ? p.total_chunks : sm_count();
-    lstm_wgrad_tc_kernel<<<(unsigned)grid, kWgThreads, kWgSmem, st>>>(p);
+    if (n == 256)
+        lstm_wgrad_tc_kernel<256><<<(unsigned)grid, kWgThreads, WgCfg<256>::kSmem, st>>>(p);
+    else
+        lstm_wgrad_tc_kernel<64><<<(unsigned)grid, kWgThreads, WgCfg<64>::kSmem, st>>>(p);
     count_launch();
-    return check_launch("lstm_wgrad_tc");
+    return check_launch("wgrad_tc");
+}
+int32_t launch_lstm_wgrad_tc(const float* seg0, const float* seg1, const float* h0, const float* da, float* dwp, int kd,
+                             int t_len, int64_t rows, cudaStream_t st) {
+    return launch_wgrad_tc(seg0, seg1, h0, 1, da, 256, dwp, kd, t_len, rows, st);
 }
 
 }  // namespace stmgcn
@@ -918,11 +831,11 @@ extern "C" int32_t stmgcn_lstm_pack_tc(const float* wp_fwd, int32_t kd_fwd, cons
                    "lstm_pack_tc: tensor-core path needs hid == 64 and kd %% 32 == 0 (got hid=%d kd=%d)", hid, kd_fwd);
     cudaStream_t st = (cudaStream_t)stream;
     // forward operand B[n = gate col][k = kd index] = wp_fwd[k][n]
-    pack_image_kernel<<<(kd_fwd * kGateCols + 255) / 256, 256, 0, st>>>(wp_fwd, kGateCols, kd_fwd, 1, kGateCols, img_fwd);
+    pack_image_kernel<<<(kd_fwd * kGateCols + 255) / 256, 256, 0, st>>>(wp_fwd, kGateCols, kd_fwd, 1, kGateCols, img_fwd, kGateCols);
     count_launch();
     if (img_bwd != nullptr) {   // backward operand B[n = kd index][k = gate col] = wp_bwd[n][k]
         STMGCN_REQUIRE(wp_bwd && (kd_bwd == 64 || kd_bwd == 128), STMGCN_ERR_SHAPE, "lstm_pack_tc: kd_bwd=%d", kd_bwd);
-        pack_image_kernel<<<(kd_bwd * kGateCols + 255) / 256, 256, 0, st>>>(wp_bwd, kd_bwd, kGateCols, kGateCols, 1, img_bwd);
+        pack_image_kernel<<<(kd_bwd * kGateCols + 255) / 256, 256, 0, st>>>(wp_bwd, kd_bwd, kGateCols, kGateCols, 1, img_bwd, kd_bwd);
         count_launch();
     }
     return check_launch("lstm_pack_tc");

@@ -129,18 +129,29 @@ def adjoint_stack_(sset: SupportSet, u: torch.Tensor) -> torch.Tensor:
     return acc
 
 
+def _proj_images(w: torch.Tensor, ks: int, p: int, need_bwd: bool):
+    """tcgen05 operand images of the projection weights (p = q = 64, ks <= 4), or (None, None)."""
+    if lstm_path() != "tc" or p != 64 or w.shape[1] != 64 or ks > 4:
+        return None, None
+    img_f = torch.empty(ks * 64 * 64 * 2, device=w.device, dtype=torch.float32)
+    img_b = torch.zeros(2 * 2 * 256 * 32, device=w.device, dtype=torch.float32) if need_bwd else None
+    _lib.check(L.stmgcn_proj_pack_tc(w.data_ptr(), ks, img_f.data_ptr(), _p(img_b), _stream()), "proj_pack_tc")
+    return img_f, img_b
+
+
 def _proj_fwd(s: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int, pool: Optional[torch.Tensor],
-              b_inner: int) -> torch.Tensor:
+              b_inner: int, wimg: Optional[torch.Tensor] = None) -> torch.Tensor:
     ks, n, b, p = s.shape
     q = w.shape[1]
     out = torch.empty((n, b, q), device=s.device, dtype=torch.float32)
     _lib.check(L.stmgcn_proj_fwd(s.data_ptr(), n * b * p, ks, n * b, p, w.data_ptr(), _p(bias), q, act,
-                                 out.data_ptr(), _p(pool), b_inner, _stream()), "proj_fwd")
+                                 out.data_ptr(), _p(pool), b_inner, _p(wimg), _stream()), "proj_fwd")
     return out
 
 
 def _proj_bwd(s: torch.Tensor, w: torch.Tensor, act: int, out: torch.Tensor, d_out: Optional[torch.Tensor],
-              d_bcast: Optional[torch.Tensor], scale: float, b_inner: int, need_bias: bool, need_u: bool):
+              d_bcast: Optional[torch.Tensor], scale: float, b_inner: int, need_bias: bool, need_u: bool,
+              wimg_t: Optional[torch.Tensor] = None):
     ks, n, b, p = s.shape
     q = w.shape[1]
     dw = torch.zeros_like(w, dtype=torch.float32)
@@ -150,7 +161,7 @@ def _proj_bwd(s: torch.Tensor, w: torch.Tensor, act: int, out: torch.Tensor, d_o
     wt = w.t().contiguous() if need_u else None
     _lib.check(L.stmgcn_proj_bwd(s.data_ptr(), n * b * p, ks, n * b, p, _p(wt), q, act, out.data_ptr(), _p(d_out),
                                  _p(d_bcast), scale, b_inner, dz.data_ptr(), dw.data_ptr(), _p(db), _p(u),
-                                 n * b * p, _stream()), "proj_bwd")
+                                 n * b * p, _p(wimg_t), _stream()), "proj_bwd")
     return dw, db, u
 
 
@@ -180,18 +191,20 @@ class ChebGCN(torch.autograd.Function):
         x, w = _f32c(x), _f32c(w)
         bias_c = _f32c(bias) if bias is not None else None
         s = build_stack(sset, x)
-        out = _proj_fwd(s, w, bias_c, act, None, x.shape[1])
+        need_grad = any(ctx.needs_input_grad)
+        img_f, img_b = _proj_images(w, sset.ks, x.shape[2], need_grad)
+        out = _proj_fwd(s, w, bias_c, act, None, x.shape[1], img_f)
         ctx.sset, ctx.act, ctx.has_bias = sset, act, bias is not None
-        if any(ctx.needs_input_grad):
-            ctx.save_for_backward(s, w, out)
+        if need_grad:
+            ctx.save_for_backward(s, w, out, img_b)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        s, w, out = ctx.saved_tensors
+        s, w, out, img_b = ctx.saved_tensors
         need_dx = ctx.needs_input_grad[0]
         d_out = _f32c(d_out)
-        dw, db, u = _proj_bwd(s, w, ctx.act, out, d_out, None, 1.0, s.shape[2], ctx.has_bias, need_dx)
+        dw, db, u = _proj_bwd(s, w, ctx.act, out, d_out, None, 1.0, s.shape[2], ctx.has_bias, need_dx, img_b)
         dx = adjoint_stack_(ctx.sset, u) if need_dx else None
         return dx, dw, db, None, None
 

@@ -298,3 +298,34 @@ def test_training_loop_like_model_trainer(tmp_path):
     assert_close(out2.cpu().numpy(), out_eval.cpu().numpy(), "checkpoint round trip", 1e-5)
     assert_close(out_eval.cpu().numpy(), O.dense_st_mgcn({k_: v.detach() for k_, v in ref.items()}, x, sups).numpy(),
                  "eval forward after training", 2e-4)
+
+
+@pytest.mark.parametrize("ks", [1, 3, 4])
+def test_projection_tensor_core_path_matches_exact_fp32_path(ks):
+    """tcgen05 projection (fwd, dZ/U, dW) vs the exact-FFMA kernels; ks = 3 exercises the odd 64-row tail block of dW."""
+    from stmgcn_b200 import ops
+    from stmgcn_b200.graph import GraphHandle, SupportSet
+    n, b, p, q = 37, 9, 64, 64                                  # 333 rows: ragged 128-row tiles
+    lap = _rand_csr(n, 0.2, 3)
+    g = GraphHandle.from_dense(torch.from_numpy(lap).to(DEV))
+    sset = SupportSet("cheb", n, ks, [g] if ks > 1 else [], torch.device(DEV))
+    gen = torch.Generator().manual_seed(ks)
+    x0 = torch.randn(n, b, p, generator=gen)
+    w0 = torch.randn(ks * p, q, generator=gen) * 0.1
+    b0 = torch.randn(q, generator=gen) * 0.1
+    proj = torch.randn(n, b, q, generator=gen).to(DEV)
+    res = {}
+    old = ops.lstm_path()
+    try:
+        for path in ("fma", "tc"):
+            ops.set_lstm_path(path)
+            x = x0.to(DEV).requires_grad_(True)
+            w = w0.to(DEV).requires_grad_(True)
+            bb = b0.to(DEV).requires_grad_(True)
+            out = ops.ChebGCN.apply(x, w, bb, sset, 1)
+            (out * proj).sum().backward()
+            res[path] = [out.detach().clone(), x.grad.clone(), w.grad.clone(), bb.grad.clone()]
+    finally:
+        ops.set_lstm_path(old)
+    for name, a, c in zip(("out", "dx", "dW", "db"), res["tc"], res["fma"]):
+        assert_close(a.cpu().numpy(), c.cpu().numpy(), f"proj tc vs fma {name}", 2e-5)
