@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
     const int lane = tid & 31;
     constexpr int kMmaWarp = kFwdEpiWarps + kFwdLoaderWarps;
 
-    if (tid == 0) init_barriers(bar, kFwdStages, kFwdEpiWarps * 32, kFwdLoaders);
+    if (tid == 0) init_barriers(bar, kFwdStages, kFwdEpiWarps * 32, kFwdLoaders / 2);   // one loader group per k-block
     if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, 512);
     for (int i = tid; i < kGateCols; i += kFwdThreads) tail->bias[i] = p.bias ? p.bias[i] : 0.f;
     tc_fence_before();
@@ -85,76 +85,65 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
     const uint32_t tmem_base = bar->tmem_base;
 
     if (warp >= kFwdEpiWarps && warp < kMmaWarp) {
-        // ===================== loaders / tf32 splitters (register ping-pong) =====================
+        // ===================== loaders / tf32 splitters =====================
+        // NOTE fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: the MEMBAR waits for every outstanding
+        // memory operation of the thread, so loads prefetched by the same thread for a later k-block would be waited
+        // for at the current k-block's fence.  Memory-level parallelism therefore comes from two independent loader
+        // GROUPS that alternate k-blocks (group g owns k-blocks g, g+2, ... of this CTA's sequence): while one group
+        // waits for its loads, the other converts / stores / fences.
         TC_PROF_DECL
+        constexpr int kGroups = 2, kGT = kFwdLoaders / kGroups, kPer = 1024 / kGT;      // float4 per thread per k-block
         const int ltid = tid - kFwdEpiWarps * 32;
-        const int c = ltid & 7, rsub = ltid >> 3;          // rows rsub + 32*i, 16-byte chunk c of the 128-byte row
-        auto load = [&](int tile, int kb, float4 (&buf)[4]) {
+        const int grp = ltid / kGT, gtid = ltid % kGT;
+        const int c = gtid & 7, rsub = gtid >> 3;          // rows rsub + (kGT/8)*i, 16-byte chunk c of the 128-byte row
+        const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total = my_tiles * p.nkb;
+        for (int j = grp; j < total; j += kGroups) {
+            const int tile = blockIdx.x + (j / p.nkb) * gridDim.x, kb = j % p.nkb;
+            float4 buf[kPer];
             if (p.aux && kb == 2) {                        // auxiliary block: modulated input columns and the constant 1
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t r = (int64_t)tile * kTileM + rsub + 32 * i;
+                for (int i = 0; i < kPer; ++i) {
+                    const int64_t r = (int64_t)tile * kTileM + rsub + (kGT / 8) * i;
                     float v[4] = {0.f, 0.f, 0.f, 0.f};
                     if (c < 2 && r < p.rows) {
                         const float sv = p.sg[(r % p.b_inner) * p.t_len + p.t];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int col = 4 * c + j;
-                            if (col < p.c_in) v[j] = p.xo[(r * p.t_len + p.t) * p.c_in + col] * sv;
-                            else if (col == p.c_in) v[j] = 1.0f;
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int col = 4 * c + jj;
+                            if (col < p.c_in) v[jj] = p.xo[(r * p.t_len + p.t) * p.c_in + col] * sv;
+                            else if (col == p.c_in) v[jj] = 1.0f;
                         }
                     }
                     buf[i] = make_float4(v[0], v[1], v[2], v[3]);
                 }
-                return;
-            }
-            const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
-            const int koff = (kb & 1) * kKB + c * 4;
+            } else {
+                const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
+                const int koff = (kb & 1) * kKB + c * 4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t r = (int64_t)tile * kTileM + rsub + 32 * i;
-                buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (seg != nullptr && r < p.rows) buf[i] = *reinterpret_cast<const float4*>(seg + r * kHid + koff);
+                for (int i = 0; i < kPer; ++i) {
+                    const int64_t r = (int64_t)tile * kTileM + rsub + (kGT / 8) * i;
+                    buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (seg != nullptr && r < p.rows) buf[i] = *reinterpret_cast<const float4*>(seg + r * kHid + koff);
+                }
             }
-        };
-        uint32_t it = 0;
-        auto process = [&](const float4 (&cur)[4], int kb) {
-            const int s = it % kFwdStages;
-            const uint32_t ph = (it / kFwdStages) & 1;
+            const int s = j % kFwdStages;
+            const uint32_t ph = (j / kFwdStages) & 1;
             mbar_wait(&bar->empty[s], ph ^ 1, 0);
             uint8_t* st = smem + (size_t)s * kFwdStageBytes;
-            if (ltid == 0) {
+            if (gtid == 0) {
                 mbar_arrive_expect_tx(&bar->full[s], 2 * kFwdBBytes);
                 const float* src = p.wimg + (size_t)kb * (2 * kFwdBBytes / 4);
                 bulk_g2s(st + 2 * kABytes, src, kFwdBBytes, &bar->full[s]);
                 bulk_g2s(st + 2 * kABytes + kFwdBBytes, src + kFwdBBytes / 4, kFwdBBytes, &bar->full[s]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = rsub + 32 * i;
-                split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), cur[i]);
+            for (int i = 0; i < kPer; ++i) {
+                const int row = rsub + (kGT / 8) * i;
+                split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), buf[i]);
             }
             fence_proxy_async_smem();
             mbar_arrive(&bar->full[s]);
-            ++it;
-        };
-        // ping-pong between two register buffers (no copies: a copy would wait for the prefetch it is hiding)
-        int tile = blockIdx.x, kb = 0;
-        bool have = tile < p.n_tiles;
-        float4 b0[4], b1[4];
-        if (have) load(tile, kb, b0);
-        while (have) {
-            int ck = kb;
-            if (++kb == p.nkb) { kb = 0; tile += gridDim.x; }
-            have = tile < p.n_tiles;
-            if (have) load(tile, kb, b1);
-            process(b0, ck);
-            if (!have) break;
-            ck = kb;
-            if (++kb == p.nkb) { kb = 0; tile += gridDim.x; }
-            have = tile < p.n_tiles;
-            if (have) load(tile, kb, b0);
-            process(b1, ck);
         }
         TC_PROF_FLUSH(0, ltid == 0)
     } else if (warp == kMmaWarp) {
@@ -301,7 +290,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
     constexpr bool l0 = (N == 64);               // layer 0 <=> kd = 64 (no layer below; carries the gate adjoint)
     const bool ds_smem = l0 && p.b_inner <= 2048;
 
-    if (tid == 0) init_barriers(bar, kBwdStages, kBwdEpiWarps * 32, kNumLoaders);
+    if (tid == 0) init_barriers(bar, kBwdStages, kBwdEpiWarps * 32, kNumLoaders / 2);     // one loader group per k-block
     if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, Cfg::kTmemCols);
     for (int i = tid; i < kLoaderWarps * kGateCols; i += kBwdThreads) {
         (&tail->s_db[0][0])[i] = 0.f;
@@ -316,38 +305,44 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
 
     if (warp >= kBwdEpiWarps && warp < kMmaWarp) {
         // ===================== loaders: BPTT pointwise -> dA -> operand tiles =====================
-        // thread <-> (unit c of the k-block, rows rsub + kRowStep*i): one LSTM cell per (i, k-block); the reads of the next
-        // k-block are issued into a second register buffer before the current one is processed.
+        // two independent loader groups alternate k-blocks (see the note in lstm_cell_tc_kernel);
+        // thread <-> (unit c of the k-block, rows rsub + kRowStep*i): one LSTM cell per (i, k-block)
         TC_PROF_DECL
+        constexpr int kGroups = 2, kGT = kNumLoaders / kGroups;
+        constexpr int kCells = kTileM * 8 / kGT;              // LSTM cells per thread per k-block
+        constexpr int kRowStep = kGT / 8;
+        static_assert(kBwdNkb % kGroups == 0, "k-blocks of a tile must split evenly over the loader groups");
         const int ltid = tid - kBwdEpiWarps * 32;
-        const int c = ltid & 7, rsub = ltid >> 3, lwarp = ltid >> 5;
-        constexpr int kCells = kTileM * 8 / kNumLoaders;      // LSTM cells per thread per k-block
-        constexpr int kRowStep = kNumLoaders / 8;
-        struct CellIn { float4 g; float dh, dh2, ct, cp, dc; };   // raw loads only: no arithmetic before use
-        auto load = [&](int tile, int kb, CellIn (&buf)[kCells]) {
-            const int unit = kb * 8 + c;
+        const int grp = ltid / kGT, gtid = ltid % kGT;
+        const int c = gtid & 7, rsub = gtid >> 3, lwarp = ltid >> 5;
+        struct CellIn { float4 g; float dh, dh2, ct, cp, dc; };
+        float xs[kCells], dxs[kCells];
+        const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total = my_tiles * kBwdNkb;
+        for (int j = grp; j < total; j += kGroups) {
+            const int tile = blockIdx.x + (j / kBwdNkb) * gridDim.x, kb = j % kBwdNkb;
+            CellIn buf[kCells];
+            {
+                const int unit = kb * 8 + c;
 #pragma unroll
-            for (int i = 0; i < kCells; ++i) {
-                const int64_t r = (int64_t)tile * kTileM + rsub + kRowStep * i;
-                buf[i].g = make_float4(0.f, 0.f, 0.f, 0.f);
-                buf[i].dh = buf[i].dh2 = buf[i].ct = buf[i].cp = buf[i].dc = 0.f;
-                if (r < p.rows) {
-                    const int64_t e = r * kHid + unit;
-                    buf[i].g = *reinterpret_cast<const float4*>(p.gates + r * kGateCols + 4 * unit);
-                    buf[i].dh = p.dh_rec[e];
-                    if (p.dh_in) buf[i].dh2 = p.dh_in[e];
-                    buf[i].ct = p.c_t[e];
-                    buf[i].cp = p.c_prev ? p.c_prev[e] : 0.f;
-                    buf[i].dc = p.dc[e];
+                for (int i = 0; i < kCells; ++i) {
+                    const int64_t r = (int64_t)tile * kTileM + rsub + kRowStep * i;
+                    buf[i].g = make_float4(0.f, 0.f, 0.f, 0.f);
+                    buf[i].dh = buf[i].dh2 = buf[i].ct = buf[i].cp = buf[i].dc = 0.f;
+                    if (r < p.rows) {
+                        const int64_t e = r * kHid + unit;
+                        buf[i].g = *reinterpret_cast<const float4*>(p.gates + r * kGateCols + 4 * unit);
+                        buf[i].dh = p.dh_rec[e];
+                        if (p.dh_in) buf[i].dh2 = p.dh_in[e];
+                        buf[i].ct = p.c_t[e];
+                        buf[i].cp = p.c_prev ? p.c_prev[e] : 0.f;
+                        buf[i].dc = p.dc[e];
+                    }
                 }
             }
-        };
-        uint32_t it = 0;
-        float xs[kCells], dxs[kCells];
-        auto process = [&](const CellIn (&cur)[kCells], int tile, int kb) {
             const int64_t row_base = (int64_t)tile * kTileM;
             const int unit = kb * 8 + c;
-            if (l0 && kb == 0) {
+            if (l0 && kb == grp) {               // this group's first k-block of the tile
 #pragma unroll
                 for (int i = 0; i < kCells; ++i) {
                     const int64_t r = row_base + rsub + kRowStep * i;
@@ -362,12 +357,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < kCells; ++i) {
                 const int64_t r = row_base + rsub + kRowStep * i;
-                const float4 g = cur[i].g;
-                const float dh = cur[i].dh + cur[i].dh2;
-                const float tc_ = tanhf_(cur[i].ct);
-                const float dcv = cur[i].dc + dh * g.w * (1.f - tc_ * tc_);
+                const float4 g = buf[i].g;
+                const float dh = buf[i].dh + buf[i].dh2;
+                const float tc_ = tanhf_(buf[i].ct);
+                const float dcv = buf[i].dc + dh * g.w * (1.f - tc_ * tc_);
                 da[i].x = dcv * g.z * g.x * (1.f - g.x);
-                da[i].y = dcv * cur[i].cp * g.y * (1.f - g.y);
+                da[i].y = dcv * buf[i].cp * g.y * (1.f - g.y);
                 da[i].z = dcv * g.x * (1.f - g.z * g.z);
                 da[i].w = dh * tc_ * g.w * (1.f - g.w);
                 if (r < p.rows) {
@@ -404,11 +399,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
                     *accx = tx;
                 }
             }
-            const int s = it % kBwdStages;
-            const uint32_t ph = (it / kBwdStages) & 1;
+            const int s = j % kBwdStages;
+            const uint32_t ph = (j / kBwdStages) & 1;
             mbar_wait(&bar->empty[s], ph ^ 1, 0);
             uint8_t* st = smem + (size_t)s * Cfg::kStageBytes;
-            if (ltid == 0) {
+            if (gtid == 0) {
                 mbar_arrive_expect_tx(&bar->full[s], 2 * Cfg::kBBytes);
                 const float* src = p.wimg_t + (size_t)kb * (2 * Cfg::kBBytes / 4);
                 bulk_g2s(st + 2 * kABytes, src, Cfg::kBBytes, &bar->full[s]);
@@ -421,7 +416,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
             }
             fence_proxy_async_smem();
             mbar_arrive(&bar->full[s]);
-            if (l0 && kb == kBwdNkb - 1) {     // gate adjoint: d s[b,t] += dxmod[r] * xo[r,t]   (STMGCN.py:44, C = 1)
+            if (gtid == 0 && kb == grp && grp == 0) {            // L2 prefetch of this CTA's next tile (contiguous rows)
+                const int nt = tile + gridDim.x;
+                if (nt < p.n_tiles) {
+                    const int64_t r0 = (int64_t)nt * kTileM;
+                    const int64_t nr = (p.rows - r0) < kTileM ? (p.rows - r0) : kTileM;
+                    prefetch_l2(p.gates + r0 * kGateCols, (uint32_t)(nr * kGateCols * 4));
+                    prefetch_l2(p.c_t + r0 * kHid, (uint32_t)(nr * kHid * 4));
+                }
+            }
+            if (l0 && kb == kBwdNkb - kGroups + grp) {     // this group's last k-block of the tile: gate adjoint partial     // gate adjoint: d s[b,t] += dxmod[r] * xo[r,t]   (STMGCN.py:44, C = 1)
 #pragma unroll
                 for (int i = 0; i < kCells; ++i) {
                     const int64_t r = row_base + rsub + kRowStep * i;
@@ -437,24 +441,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
                     }
                 }
             }
-            ++it;
-        };
-        int tile = blockIdx.x, kb = 0;
-        bool have = tile < p.n_tiles;
-        CellIn b0[kCells], b1[kCells];
-        if (have) load(tile, kb, b0);
-        while (have) {
-            int ct = tile, ck = kb;
-            if (++kb == kBwdNkb) { kb = 0; tile += gridDim.x; }
-            have = tile < p.n_tiles;
-            if (have) load(tile, kb, b1);
-            process(b0, ct, ck);
-            if (!have) break;
-            ct = tile; ck = kb;
-            if (++kb == kBwdNkb) { kb = 0; tile += gridDim.x; }
-            have = tile < p.n_tiles;
-            if (have) load(tile, kb, b0);
-            process(b1, ct, ck);
         }
         TC_PROF_FLUSH((N == 128 ? 3 : 6), ltid == 0)
     } else if (warp == kMmaWarp) {
@@ -571,7 +557,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
 
     if (tid == 0) {
         for (int s = 0; s < kWgStages; ++s) {
-            mbar_init(&tail->full[s], kLoaders);
+            mbar_init(&tail->full[s], kLoaders / 2);       // one loader group per chunk
             mbar_init(&tail->empty[s], 1);
         }
         mbar_init(&tail->done, 1);
@@ -587,64 +573,48 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
     if (warp < kMmaWarp) {
         // ===================== loaders: HBM rows -> tf32 hi/lo -> MN-major swizzled atoms =====================
         TC_PROF_DECL
-        const int ltid = tid;
-        constexpr int kNA = 1024 / kLoaders, kNB = (32 * N / 4) / kLoaders, kQStep = kLoaders / 32;
+        // two loader groups alternate row chunks (see the note in lstm_cell_tc_kernel about the proxy fence)
+        constexpr int kGroups = 2, kGT = kLoaders / kGroups;
+        constexpr int kNA = 1024 / kGT, kNB = (32 * N / 4) / kGT, kQStep = kGT / 32;
         static_assert(kNB >= 1, "loader mapping");
-        struct Buf { float4 a[kNA]; float4 b[kNB]; };
-        auto load = [&](int64_t chunk, Buf& buf) {
+        const int ltid = tid;
+        const int grp = ltid / kGT, gtid = ltid % kGT;
+        const int row = gtid & 31, q0 = gtid >> 5;          // lane <-> row (K index); q0 + kQStep*i: float4 along M / N
+        const int64_t my_chunks = (p.total_chunks - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;
+        for (int64_t j = grp; j < my_chunks; j += kGroups) {
+            const int64_t chunk = blockIdx.x + j * gridDim.x;
             const int t = (int)(chunk / p.chunks_per_t);
-            const int64_t r0 = (chunk % p.chunks_per_t) * kWgRows;
+            const int64_t r = (chunk % p.chunks_per_t) * kWgRows + row;
             const float* s0 = p.seg0 ? p.seg0 + (int64_t)t * p.rows * kHid : nullptr;
             const float* s1 = p.shift1 ? ((t > 0) ? p.seg1 + (int64_t)(t - 1) * p.rows * kHid : p.h0)
                                         : p.seg1 + (int64_t)t * p.rows * kHid;
             const float* dt = p.da + (int64_t)t * p.rows * N;
+            float4 va[kNA], vb[kNB];
 #pragma unroll
             for (int i = 0; i < kNA; ++i) {
-                const int row = ltid & 31, q = (ltid >> 5) + kQStep * i;   // lane <-> row (K index), q: float4 along M
-                const int64_t r = r0 + row;
+                const int q = q0 + kQStep * i;
                 // kd = 128: m 0..63 from seg0 (h_below), 64..127 from seg1 (h_prev); kd = 64: m 0..63 from seg1
                 const float* src = (p.kd == 128) ? (q < 16 ? s0 : s1) : (q < 16 ? s1 : nullptr);
-                buf.a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (src != nullptr && r < p.rows) buf.a[i] = *reinterpret_cast<const float4*>(src + r * kHid + (q & 15) * 4);
+                va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src != nullptr && r < p.rows) va[i] = *reinterpret_cast<const float4*>(src + r * kHid + (q & 15) * 4);
             }
 #pragma unroll
             for (int i = 0; i < kNB; ++i) {
-                const int row = ltid & 31, q = (ltid >> 5) + kQStep * i;   // q: float4 along N (64 per row)
-                const int64_t r = r0 + row;
-                buf.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < p.rows) buf.b[i] = *reinterpret_cast<const float4*>(dt + r * N + q * 4);
+                const int q = q0 + kQStep * i;
+                vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < p.rows) vb[i] = *reinterpret_cast<const float4*>(dt + r * N + q * 4);
             }
-        };
-        uint32_t it = 0;
-        auto process = [&](const Buf& cur) {
-            const int s = it % kWgStages;
-            const uint32_t ph = (it / kWgStages) & 1;
+            const int s = (int)(j % kWgStages);
+            const uint32_t ph = (uint32_t)(j / kWgStages) & 1;
             mbar_wait(&tail->empty[s], ph ^ 1, 0);
             uint8_t* st = smem + (size_t)s * kWgStageBytes;
 #pragma unroll
-            for (int i = 0; i < kNA; ++i)
-                split_store_t(st, st + kWgABytes, 4 * ((ltid >> 5) + kQStep * i), ltid & 31, cur.a[i]);
+            for (int i = 0; i < kNA; ++i) split_store_t(st, st + kWgABytes, 4 * (q0 + kQStep * i), row, va[i]);
 #pragma unroll
             for (int i = 0; i < kNB; ++i)
-                split_store_t(st + 2 * kWgABytes, st + 2 * kWgABytes + kWgBBytes, 4 * ((ltid >> 5) + kQStep * i), ltid & 31, cur.b[i]);
+                split_store_t(st + 2 * kWgABytes, st + 2 * kWgABytes + kWgBBytes, 4 * (q0 + kQStep * i), row, vb[i]);
             fence_proxy_async_smem();
             mbar_arrive(&tail->full[s]);
-            ++it;
-        };
-        int64_t chunk = blockIdx.x;
-        bool have = chunk < p.total_chunks;
-        Buf b0, b1;
-        if (have) load(chunk, b0);
-        while (have) {
-            chunk += gridDim.x;
-            have = chunk < p.total_chunks;
-            if (have) load(chunk, b1);
-            process(b0);
-            if (!have) break;
-            chunk += gridDim.x;
-            have = chunk < p.total_chunks;
-            if (have) load(chunk, b0);
-            process(b1);
         }
         TC_PROF_FLUSH(9, ltid == 0)
         // ===================== epilogue (warps 0-3): accumulator rows = kd index -> red.add into dWp =====================

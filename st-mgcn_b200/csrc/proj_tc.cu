@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(PCfg<N>::kThreads, 1) proj_rows_tc_kernel(cons
     const int lane = tid & 31;
     constexpr int kMmaWarp = Cfg::kEpiWarps + kPLoaderWarps;
 
-    if (tid == 0) init_barriers(bar, Cfg::kStages, Cfg::kEpiWarps * 32, kPLoaders);
+    if (tid == 0) init_barriers(bar, Cfg::kStages, Cfg::kEpiWarps * 32, kPLoaders / 2);   // one loader group per k-block
     if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, Cfg::kTmemCols);
     for (int i = tid; i < 64; i += Cfg::kThreads) tail->bias[i] = (!DZ && p.bias) ? p.bias[i] : 0.f;
     for (int i = tid; i < kPLoaderWarps * 64; i += Cfg::kThreads) (&tail->s_db[0][0])[i] = 0.f;
@@ -75,44 +75,36 @@ __global__ void __launch_bounds__(PCfg<N>::kThreads, 1) proj_rows_tc_kernel(cons
     const uint32_t tmem_base = bar->tmem_base;
 
     if (warp >= Cfg::kEpiWarps && warp < kMmaWarp) {
-        // ===================== loaders =====================
+        // ===================== loaders: two groups alternate k-blocks (see lstm_tc.cu on the proxy fence) ==========
         TC_PROF_DECL
+        constexpr int kGroups = 2, kGT = kPLoaders / kGroups, kPer = 1024 / kGT;
         const int ltid = tid - Cfg::kEpiWarps * 32;
-        const int c = ltid & 7, rsub = ltid >> 3, lwarp = ltid >> 5;
-        struct Buf { float4 v[4]; float4 m[4]; };
-        auto load = [&](int tile, int kb, Buf& buf) {
+        const int grp = ltid / kGT, gtid = ltid % kGT;
+        const int c = gtid & 7, rsub = gtid >> 3, lwarp = ltid >> 5;
+        const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total = my_tiles * p.nkb;
+        for (int j = grp; j < total; j += kGroups) {
+            const int tile = blockIdx.x + (j / p.nkb) * gridDim.x, kb = j % p.nkb;
             const int koff = (kb & 1) * kKB + c * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t r = (int64_t)tile * kTileM + rsub + 32 * i;
-                buf.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                buf.m[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (r < p.rows) {
-                    if (DZ) {
-                        buf.v[i] = *reinterpret_cast<const float4*>(p.d_out + r * 64 + koff);
-                        if (p.act == STMGCN_ACT_RELU) buf.m[i] = *reinterpret_cast<const float4*>(p.out_act + r * 64 + koff);
-                    } else {
-                        const float* seg = p.seg[kb >> 1];
-                        if (seg != nullptr) buf.v[i] = *reinterpret_cast<const float4*>(seg + r * 64 + koff);
-                    }
-                }
-            }
-        };
-        uint32_t it = 0;
-        auto process = [&](Buf& cur, int tile, int kb) {
+            float4 v[kPer];
             if (DZ) {
                 float4 sb = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int koff = (kb & 1) * kKB + c * 4;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t r = (int64_t)tile * kTileM + rsub + 32 * i;
-                    float4 d = cur.v[i];
-                    if (!(cur.m[i].x > 0.f)) d.x = 0.f;
-                    if (!(cur.m[i].y > 0.f)) d.y = 0.f;
-                    if (!(cur.m[i].z > 0.f)) d.z = 0.f;
-                    if (!(cur.m[i].w > 0.f)) d.w = 0.f;
-                    cur.v[i] = d;
-                    if (r < p.rows) *reinterpret_cast<float4*>(p.dz_out + r * 64 + koff) = d;
+                for (int i = 0; i < kPer; ++i) {
+                    const int64_t r = (int64_t)tile * kTileM + rsub + (kGT / 8) * i;
+                    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < p.rows) {
+                        d = *reinterpret_cast<const float4*>(p.d_out + r * 64 + koff);
+                        if (p.act == STMGCN_ACT_RELU) {
+                            const float4 m = *reinterpret_cast<const float4*>(p.out_act + r * 64 + koff);
+                            if (!(m.x > 0.f)) d.x = 0.f;
+                            if (!(m.y > 0.f)) d.y = 0.f;
+                            if (!(m.z > 0.f)) d.z = 0.f;
+                            if (!(m.w > 0.f)) d.w = 0.f;
+                        }
+                        *reinterpret_cast<float4*>(p.dz_out + r * 64 + koff) = d;
+                    }
+                    v[i] = d;
                     sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
                 }
 #pragma unroll
@@ -126,42 +118,32 @@ __global__ void __launch_bounds__(PCfg<N>::kThreads, 1) proj_rows_tc_kernel(cons
                     t.x += sb.x; t.y += sb.y; t.z += sb.z; t.w += sb.w;
                     *acc = t;
                 }
+            } else {
+                const float* seg = p.seg[kb >> 1];
+#pragma unroll
+                for (int i = 0; i < kPer; ++i) {
+                    const int64_t r = (int64_t)tile * kTileM + rsub + (kGT / 8) * i;
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (seg != nullptr && r < p.rows) v[i] = *reinterpret_cast<const float4*>(seg + r * 64 + koff);
+                }
             }
-            const int s = it % Cfg::kStages;
-            const uint32_t ph = (it / Cfg::kStages) & 1;
+            const int s = j % Cfg::kStages;
+            const uint32_t ph = (j / Cfg::kStages) & 1;
             mbar_wait(&bar->empty[s], ph ^ 1, 0);
             uint8_t* st = smem + (size_t)s * Cfg::kStageBytes;
-            if (ltid == 0) {
+            if (gtid == 0) {
                 mbar_arrive_expect_tx(&bar->full[s], 2 * Cfg::kBBytes);
                 const float* src = p.wimg + (size_t)kb * (2 * Cfg::kBBytes / 4);
                 bulk_g2s(st + 2 * kABytes, src, Cfg::kBBytes, &bar->full[s]);
                 bulk_g2s(st + 2 * kABytes + Cfg::kBBytes, src + Cfg::kBBytes / 4, Cfg::kBBytes, &bar->full[s]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = rsub + 32 * i;
-                split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), cur.v[i]);
+            for (int i = 0; i < kPer; ++i) {
+                const int row = rsub + (kGT / 8) * i;
+                split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), v[i]);
             }
             fence_proxy_async_smem();
             mbar_arrive(&bar->full[s]);
-            ++it;
-        };
-        int tile = blockIdx.x, kb = 0;
-        bool have = tile < p.n_tiles;
-        Buf b0, b1;
-        if (have) load(tile, kb, b0);
-        while (have) {
-            int ct = tile, ck = kb;
-            if (++kb == p.nkb) { kb = 0; tile += gridDim.x; }
-            have = tile < p.n_tiles;
-            if (have) load(tile, kb, b1);
-            process(b0, ct, ck);
-            if (!have) break;
-            ct = tile; ck = kb;
-            if (++kb == p.nkb) { kb = 0; tile += gridDim.x; }
-            have = tile < p.n_tiles;
-            if (have) load(tile, kb, b0);
-            process(b1, ct, ck);
         }
         TC_PROF_FLUSH(11, ltid == 0)
     } else if (warp == kMmaWarp) {
