@@ -579,28 +579,32 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
         static_assert(kNB >= 1, "loader mapping");
         const int ltid = tid;
         const int grp = ltid / kGT, gtid = ltid % kGT;
-        const int row = gtid & 31, q0 = gtid >> 5;          // lane <-> row (K index); q0 + kQStep*i: float4 along M / N
+        const int my_chunks_dummy = 0; (void)my_chunks_dummy;
         const int64_t my_chunks = (p.total_chunks - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;
         for (int64_t j = grp; j < my_chunks; j += kGroups) {
             const int64_t chunk = blockIdx.x + j * gridDim.x;
             const int t = (int)(chunk / p.chunks_per_t);
-            const int64_t r = (chunk % p.chunks_per_t) * kWgRows + row;
+            const int64_t r0 = (chunk % p.chunks_per_t) * kWgRows;
             const float* s0 = p.seg0 ? p.seg0 + (int64_t)t * p.rows * kHid : nullptr;
             const float* s1 = p.shift1 ? ((t > 0) ? p.seg1 + (int64_t)(t - 1) * p.rows * kHid : p.h0)
                                         : p.seg1 + (int64_t)t * p.rows * kHid;
             const float* dt = p.da + (int64_t)t * p.rows * N;
             float4 va[kNA], vb[kNB];
 #pragma unroll
-            for (int i = 0; i < kNA; ++i) {
-                const int q = q0 + kQStep * i;
+            for (int i = 0; i < kNA; ++i) {                   // A': 32 rows x 32 float4 (128 kd values), coalesced
+                const int idx = gtid + i * kGT;
+                const int row = idx >> 5, q = idx & 31;
+                const int64_t r = r0 + row;
                 // kd = 128: m 0..63 from seg0 (h_below), 64..127 from seg1 (h_prev); kd = 64: m 0..63 from seg1
                 const float* src = (p.kd == 128) ? (q < 16 ? s0 : s1) : (q < 16 ? s1 : nullptr);
                 va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (src != nullptr && r < p.rows) va[i] = *reinterpret_cast<const float4*>(src + r * kHid + (q & 15) * 4);
             }
 #pragma unroll
-            for (int i = 0; i < kNB; ++i) {
-                const int q = q0 + kQStep * i;
+            for (int i = 0; i < kNB; ++i) {                   // B': 32 rows x N/4 float4, coalesced
+                const int idx = gtid + i * kGT;
+                const int row = idx / (N / 4), q = idx % (N / 4);
+                const int64_t r = r0 + row;
                 vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (r < p.rows) vb[i] = *reinterpret_cast<const float4*>(dt + r * N + q * 4);
             }
@@ -609,10 +613,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
             mbar_wait(&tail->empty[s], ph ^ 1, 0);
             uint8_t* st = smem + (size_t)s * kWgStageBytes;
 #pragma unroll
-            for (int i = 0; i < kNA; ++i) split_store_t(st, st + kWgABytes, 4 * (q0 + kQStep * i), row, va[i]);
+            for (int i = 0; i < kNA; ++i) {
+                const int idx = gtid + i * kGT;
+                split_store(st, mn32_offset(idx & 31, idx >> 5, kWgRows), va[i]);      // hi at st, lo at st + kWgABytes
+            }
 #pragma unroll
-            for (int i = 0; i < kNB; ++i)
-                split_store_t(st + 2 * kWgABytes, st + 2 * kWgABytes + kWgBBytes, 4 * (q0 + kQStep * i), row, vb[i]);
+            for (int i = 0; i < kNB; ++i) {
+                const int idx = gtid + i * kGT;
+                const uint32_t off = mn32_offset(idx % (N / 4), idx / (N / 4), kWgRows);
+                float4 hi, lo;
+                const float4 v = vb[i];
+                hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+                lo.x = tf32_lo(v.x, hi.x); lo.y = tf32_lo(v.y, hi.y); lo.z = tf32_lo(v.z, hi.z); lo.w = tf32_lo(v.w, hi.w);
+                *reinterpret_cast<float4*>(st + 2 * kWgABytes + off) = hi;
+                *reinterpret_cast<float4*>(st + 2 * kWgABytes + kWgBBytes + off) = lo;
+            }
             fence_proxy_async_smem();
             mbar_arrive(&tail->full[s]);
         }
@@ -636,7 +651,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
         }
     } else {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = idesc_tf32(128, N);
+        constexpr uint32_t idesc = idesc_tf32(128, N, 1);          // both operands MN-major
+        constexpr uint32_t kLbo = (kWgRows / 4) * 512, kSbo = 512;
         TC_PROF_DECL
         uint32_t it = 0;
         for (int64_t chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x, ++it) {
@@ -651,10 +667,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
                     const uint32_t a_base = st + ((pass == 1) ? kWgABytes : 0);
                     const uint32_t b_base = st + 2 * kWgABytes + ((pass == 2) ? kWgBBytes : 0);
 #pragma unroll
-                    const uint64_t da = smem_desc_k_sw128(a_base), db = smem_desc_k_sw128(b_base);
-                    for (int ks = 0; ks < kWgRows / 8; ++ks)
-                        mma_tf32(tmem_base, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc,
-                                 (it > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+                    for (int ks = 0; ks < kWgRows / 8; ++ks) {      // one MMA consumes K = 8 rows = two 4-row atoms
+                        const uint64_t da = smem_desc_mn_sw128(a_base + ks * 2 * kSbo, kLbo, kSbo, 1);
+                        const uint64_t db = smem_desc_mn_sw128(b_base + ks * 2 * kSbo, kLbo, kSbo, 1);
+                        mma_tf32(tmem_base, da, db, idesc, (it > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+                    }
                 }
                 mma_commit(&tail->empty[s]);
             }
