@@ -322,8 +322,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
         for (int j = grp; j < total; j += kGroups) {
             const int tile = blockIdx.x + (j / kBwdNkb) * gridDim.x, kb = j % kBwdNkb;
             CellIn buf[kCells];
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
             {
                 const int unit = kb * 8 + c;
+                if (l0) {
+                    wv = __ldg(reinterpret_cast<const float4*>(p.wx + 4 * unit));
+                    if (kb == grp) {               // this group's first k-block of the tile: modulated inputs of its rows
+#pragma unroll
+                        for (int i = 0; i < kCells; ++i) {
+                            const int64_t r = (int64_t)tile * kTileM + rsub + kRowStep * i;
+                            xs[i] = (r < p.rows) ? p.xo[(r * p.t_len + p.t) * p.c_in] * p.sg[(r % p.b_inner) * p.t_len + p.t] : 0.f;
+                            dxs[i] = 0.f;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < kCells; ++i) {
                     const int64_t r = (int64_t)tile * kTileM + rsub + kRowStep * i;
@@ -342,18 +354,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
             }
             const int64_t row_base = (int64_t)tile * kTileM;
             const int unit = kb * 8 + c;
-            if (l0 && kb == grp) {               // this group's first k-block of the tile
-#pragma unroll
-                for (int i = 0; i < kCells; ++i) {
-                    const int64_t r = row_base + rsub + kRowStep * i;
-                    xs[i] = (r < p.rows) ? p.xo[(r * p.t_len + p.t) * p.c_in] * p.sg[(r % p.b_inner) * p.t_len + p.t] : 0.f;
-                    dxs[i] = 0.f;
-                }
-            }
             float4 da[kCells];
+            float dcn[kCells];
             float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sx = sb;
-            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (l0) wv = __ldg(reinterpret_cast<const float4*>(p.wx + 4 * unit));
 #pragma unroll
             for (int i = 0; i < kCells; ++i) {
                 const int64_t r = row_base + rsub + kRowStep * i;
@@ -365,10 +368,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
                 da[i].y = dcv * buf[i].cp * g.y * (1.f - g.y);
                 da[i].z = dcv * g.x * (1.f - g.z * g.z);
                 da[i].w = dh * tc_ * g.w * (1.f - g.w);
-                if (r < p.rows) {
-                    p.dc[r * kHid + unit] = dcv * g.y;
-                    *reinterpret_cast<float4*>(p.gates + r * kGateCols + 4 * unit) = da[i];
-                }
+                dcn[i] = dcv * g.y;
                 sb.x += da[i].x; sb.y += da[i].y; sb.z += da[i].z; sb.w += da[i].w;
                 if (l0) {
                     sx.x = fmaf(xs[i], da[i].x, sx.x); sx.y = fmaf(xs[i], da[i].y, sx.y);
@@ -416,6 +416,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
             }
             fence_proxy_async_smem();
             mbar_arrive(&bar->full[s]);
+            // tape updates AFTER the hand-off: the proxy fence (MEMBAR.ALL.CTA) of the NEXT k-block is the first point
+            // that waits for these stores, a whole iteration later
+#pragma unroll
+            for (int i = 0; i < kCells; ++i) {
+                const int64_t r = row_base + rsub + kRowStep * i;
+                if (r < p.rows) {
+                    p.dc[r * kHid + unit] = dcn[i];
+                    *reinterpret_cast<float4*>(p.gates + r * kGateCols + 4 * unit) = da[i];
+                }
+            }
             if (gtid == 0 && kb == grp && grp == 0) {            // L2 prefetch of this CTA's next tile (contiguous rows)
                 const int nt = tile + gridDim.x;
                 if (nt < p.n_tiles) {

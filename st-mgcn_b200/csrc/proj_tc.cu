@@ -102,7 +102,6 @@ __global__ void __launch_bounds__(PCfg<N>::kThreads, 1) proj_rows_tc_kernel(cons
                             if (!(m.z > 0.f)) d.z = 0.f;
                             if (!(m.w > 0.f)) d.w = 0.f;
                         }
-                        *reinterpret_cast<float4*>(p.dz_out + r * 64 + koff) = d;
                     }
                     v[i] = d;
                     sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
@@ -144,6 +143,13 @@ __global__ void __launch_bounds__(PCfg<N>::kThreads, 1) proj_rows_tc_kernel(cons
             }
             fence_proxy_async_smem();
             mbar_arrive(&bar->full[s]);
+            if (DZ) {          // dZ tape for the weight-gradient kernel, stored after the hand-off (see lstm_tc.cu)
+#pragma unroll
+                for (int i = 0; i < kPer; ++i) {
+                    const int64_t r = (int64_t)tile * kTileM + rsub + (kGT / 8) * i;
+                    if (r < p.rows) *reinterpret_cast<float4*>(p.dz_out + r * 64 + koff) = v[i];
+                }
+            }
         }
         TC_PROF_FLUSH(11, ltid == 0)
     } else if (warp == kMmaWarp) {
