@@ -307,32 +307,58 @@ def run_ours(args, w):
                 ops.cheb_stack_(sset, st)
                 ops.cheb_stack_(sset, ss)
 
-        for _ in range(3):
-            spmm_forward_all()
-        reps = 5
-        l1 = _lib.launch_count()
-        ms_spmm = timed(lambda: spmm_forward_all(), reps) / reps if world == 1 else None
-        if ms_spmm is None:      # multi-GPU run: time locally without collectives
+        def spmm_dominant():                    # the dominant launch type: spatial recurrence step k >= 2, all graphs
+            for sset, (st, ss) in zip(ssets, stacks):
+                g = sset.graphs[0]
+                for k in range(2, w.n_supports):
+                    ops.spmm_step(g, False, 2.0, ss[k - 1], -1.0, ss[k - 2], 0.0, None, ss[k])
+
+        def time_local(fn, reps):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(reps):
-                spmm_forward_all()
+                fn()
             e1.record()
             torch.cuda.synchronize()
-            ms_spmm = e0.elapsed_time(e1) / reps
+            return e0.elapsed_time(e1) / reps
+
+        for _ in range(3):
+            spmm_forward_all()
+        reps = 5
+        l1 = _lib.launch_count()
+        ms_spmm = time_local(spmm_forward_all, reps)
         n_launch = (_lib.launch_count() - l1) // reps
         alg = sum(spmm_algorithmic_bytes(n, s.graphs[0].nnz if s.graphs else 0, b * f, k_ord)
                   for s in ssets for f in (w.seq_len, w.lstm_hidden))
-        achieved = alg / (ms_spmm * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "spmm_row_gather_kernel (Chebyshev recurrence step)",
+        l2 = _lib.launch_count()
+        ms_dom = time_local(spmm_dominant, reps) if k_ord >= 2 else None
+        n_dom = (_lib.launch_count() - l2) // reps
+        f_sp = b * w.lstm_hidden
+        alg_dom = [s.graphs[0].nnz * 8 + (n + 1) * 4 + n * f_sp * 4 * 3 for s in ssets]       # r_k = 2 reads + 1 write
+        if ms_dom:
+            us_launch = ms_dom * 1e3 / max(n_dom, 1)
+            achieved = (sum(alg_dom) * (k_ord - 1)) / (ms_dom * 1e-3) / 1e9
+        else:
+            us_launch, achieved = ms_spmm * 1e3 / max(n_launch, 1), alg / (ms_spmm * 1e-3) / 1e9
+        # DRAM bytes per launch of this launch type from the committed ncu --set full capture (profiles/): only valid
+        # for the exact shape it was captured on (cfg3, batch 64)
+        traffic = 183.4e6 if (w.name == "cfg3" and b == 64) else None
+        roofline = {"bound": "hbm", "kernel": "spmm_row_gather_kernel<4> (Chebyshev recurrence step, spatial, k>=2)",
                     "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                    "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
-                    "algorithmic_bytes_per_forward": alg, "launches_per_forward": n_launch,
-                    "ms_per_forward": ms_spmm, "avg_us_per_launch": ms_spmm * 1e3 / max(n_launch, 1),
-                    "scope": f"all {n_launch} forward recurrence launches of one step ({w.n_graphs} graphs x "
-                             f"(temporal F={b * w.seq_len} + spatial F={b * w.lstm_hidden}) x K={k_ord}), timed alone with "
-                             f"CUDA events; bytes per SURVEY.md 8(d)"}
+                    "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                    "traffic_source": "profiles/r1_spmm_v1_ncu_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum, "
+                                      "per launch (136.0 + 47.4 MB)" if traffic else None,
+                    "algorithmic_bytes_per_launch": sum(alg_dom) / len(alg_dom), "avg_us_per_launch": us_launch,
+                    "launches_timed": n_dom,
+                    "forward_all": {"algorithmic_bytes": alg, "launches": n_launch, "ms": ms_spmm,
+                                    "achieved_gbs": alg / (ms_spmm * 1e-3) / 1e9,
+                                    "frac": alg / (ms_spmm * 1e-3) / 1e9 / pk["hbm_gbs"]},
+                    "scope": f"per launch: Y = 2 L X - Z on (N={n}, F={f_sp}) fp32, bytes = nnz*8 + (N+1)*4 + 3*N*F*4 "
+                             f"(SURVEY.md 8(d)); timed alone with CUDA events over {n_dom} launches ({w.n_graphs} graphs x "
+                             f"k=2..{k_ord}); forward_all = all {n_launch} recurrence launches of one forward "
+                             f"(temporal F={b * w.seq_len} + spatial F={f_sp}). The kernel is bound by its L2 gather volume "
+                             f"nnz*F*4 B per launch (see DESIGN.md section 3), not by HBM"}
         del stacks
 
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ------------------------------------------
