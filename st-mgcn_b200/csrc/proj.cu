@@ -102,6 +102,52 @@ dz_kernel(const float* __restrict__ out, const float* __restrict__ d_out, const 
         for (int e = threadIdx.x; e < q; e += blockDim.x) atomicAdd(&dbias[e], s_db[e]);
 }
 
+// dW (kd x q) += S^T dZ for SMALL kd*q (the temporal GCN: kd = Ks*T = 48, q = T = 12): each CTA streams row chunks of
+// S and dZ through shared memory; thread e owns outputs e, e + blockDim, ...  (i = out / q, j = out % q).
+constexpr int kSmallRows = 64;
+constexpr int kSmallThreads = 256;
+constexpr int kSmallMaxPerThread = 8;
+__global__ void __launch_bounds__(kSmallThreads)
+small_wgrad_kernel(ASegs a, int64_t rows, int kd, const float* __restrict__ dz, int q, float* __restrict__ dw) {
+    extern __shared__ float sm[];                    // S chunk [kSmallRows][kd] | dZ chunk [kSmallRows][q]
+    float* ss = sm;
+    float* ds = sm + kSmallRows * kd;
+    const int n_out = kd * q;
+    float acc[kSmallMaxPerThread];
+#pragma unroll
+    for (int o = 0; o < kSmallMaxPerThread; ++o) acc[o] = 0.f;
+    for (int64_t r0 = (int64_t)blockIdx.x * kSmallRows; r0 < rows; r0 += (int64_t)gridDim.x * kSmallRows) {
+        for (int e = threadIdx.x; e < kSmallRows * kd; e += kSmallThreads) {
+            const int rr = e / kd, k = e % kd;
+            const int sg = k / a.segw;
+            const int64_t r = r0 + rr;
+            ss[e] = (r < rows && a.seg[sg]) ? a.seg[sg][r * a.lda + (k - sg * a.segw)] : 0.f;
+        }
+        for (int e = threadIdx.x; e < kSmallRows * q; e += kSmallThreads) {
+            const int64_t r = r0 + e / q;
+            ds[e] = r < rows ? dz[r * q + e % q] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int o = 0; o < kSmallMaxPerThread; ++o) {
+            const int out = threadIdx.x + o * kSmallThreads;
+            if (out < n_out) {
+                const int i = out / q, j = out % q;
+                float s_acc = acc[o];
+#pragma unroll 8
+                for (int rr = 0; rr < kSmallRows; ++rr) s_acc = fmaf(ss[rr * kd + i], ds[rr * q + j], s_acc);
+                acc[o] = s_acc;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 0; o < kSmallMaxPerThread; ++o) {
+        const int out = threadIdx.x + o * kSmallThreads;
+        if (out < n_out) atomicAdd(&dw[out], acc[o]);
+    }
+}
+
 template <class Epi>
 int32_t launch_tall_auto(const ASegs& a, int64_t rows, int kd, const float* b, int ldb, int nc, Epi epi,
                          cudaStream_t st, const char* what) {
@@ -211,7 +257,21 @@ int32_t stmgcn_proj_bwd(const float* s, int64_t stride_k, int32_t ks, int64_t ro
         count_launch();
         if (int32_t rc = check_launch("proj_bwd dz")) return rc;
     }
-    {   // dW (ks*p, q) += S^T dZ
+    if (ks * p * q <= kSmallThreads * kSmallMaxPerThread && (size_t)kSmallRows * (ks * p + q) * 4 <= 48 * 1024) {
+        // small outputs (temporal GCN): dedicated streaming kernel instead of the 512-row-tile reduce GEMM
+        ASegs a{};
+        a.nseg = ks;
+        a.segw = p;
+        a.lda = p;
+        for (int k = 0; k < ks; ++k) a.seg[k] = s + (int64_t)k * stride_k;
+        int64_t blocks = ceil_div(rows, kSmallRows);
+        const int64_t cap = (int64_t)sm_count() * 4;
+        if (blocks > cap) blocks = cap;
+        small_wgrad_kernel<<<(unsigned)blocks, kSmallThreads, (size_t)kSmallRows * (ks * p + q) * 4, st>>>(
+            a, rows, ks * p, dz_work, q, dw);
+        count_launch();
+        if (int32_t rc = check_launch("proj_bwd dW(small)")) return rc;
+    } else {   // dW (ks*p, q) += S^T dZ
         ASegs a{};
         a.nseg = ks;
         a.segw = p;
