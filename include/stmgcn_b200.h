@@ -147,13 +147,16 @@ int32_t stmgcn_lstm_pack_tc(const float* wp_fwd, int32_t kd_fwd, const float* wp
  * Workspaces, zeroed by the caller before t = T-1: dh_rec, dc: (L, R, H); dx_work: (R, H).
  * gates[l][t] is overwritten IN PLACE with the pre-activation gradients dA (stmgcn_lstm_wgrad reads them).
  * wimg_t: optional per-layer tensor-core images of Wp^T (stmgcn_lstm_pack_tc) or NULL.
+ * blocked_ws != 0 (tensor-core kernels on every layer only): d_top, dh_rec, dc, dx_work are tile-blocked,
+ * element (r, u) at (((r/128)*8 + u/8)*128 + r%128)*8 + u%8, with ceil(R/128)*128 rows per (layer) slice.
  * Accumulates (+=; caller zeroes): d_s (B,T) = sum_{n,c} dxmod * xo (gate adjoint, STMGCN.py:44),
  * dwx (C,4H), dbp[l] (4H). */
 int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
                              const float* wx, const float* const* wpt, const float* const* wimg_t,
                              const float* c0, const float* cs, float* gates, const float* d_top, float* dh_rec,
-                             float* dc, float* dx_work, float* d_s, float* dwx, float* const* dbp, void* stream);
+                             float* dc, float* dx_work, float* d_s, float* dwx, float* const* dbp,
+                             int32_t blocked_ws, void* stream);
 /* weight gradients of one layer after all stmgcn_lstm_step_bwd calls:
  * dwp (kd_l, 4H) += [h_below_t | h_{t-1}]^T dA summed over all (t, r).  use_tc != 0 (and H = 64) runs the
  * tcgen05 3xTF32 kernel, otherwise the exact-FFMA reduction. */

@@ -19,7 +19,7 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
 int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* c_prev, const float* dh_in,
                            float* dh_rec, float* dc, float* dx_out, const float* wimg_t, float* dbp, const float* wx,
                            float* dwx, const float* xo, const float* sg, float* d_s, int c_in, int t, int t_len,
-                           int64_t b_inner, int64_t rows, cudaStream_t st);
+                           int64_t b_inner, int64_t rows, int blocked, cudaStream_t st);
 int lstm_tc_max_c_bwd();
 int32_t launch_lstm_wgrad_tc(const float* seg0, const float* seg1, const float* h0, const float* da, float* dwp, int kd,
                              int t_len, int64_t rows, cudaStream_t st);
@@ -325,13 +325,16 @@ int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
                              const float* wx, const float* const* wpt, const float* const* wimg_t,
                              const float* c0, const float* cs, float* gates, const float* d_top, float* dh_rec,
-                             float* dc, float* dx_work, float* d_s, float* dwx, float* const* dbp, void* stream) {
+                             float* dc, float* dx_work, float* d_s, float* dwx, float* const* dbp, int32_t blocked_ws,
+                             void* stream) {
     STMGCN_REQUIRE(xo && s_gate && wx && wpt && cs && gates && dh_rec && dc && dx_work && d_s && dwx && dbp,
                    STMGCN_ERR_ARG, "lstm_step_bwd: null pointer");
     if (int32_t rc = check_dims("lstm_step_bwd", t, t_len, n_layers, rows, hid, c_in, b_inner)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t rh = rows * hid;
     const int h4 = 4 * hid;
+    // workspaces dh_rec / dc hold ceil(rows/128)*128 rows per layer when tile-blocked (tensor-core kernels only)
+    const int64_t ws_rh = blocked_ws ? ceil_div(rows, 128) * 128 * hid : rh;
     const int grid_pw = (int)((ceil_div(rows, 8) < (int64_t)sm_count() * 4) ? ceil_div(rows, 8) : (int64_t)sm_count() * 4);
     for (int l = n_layers - 1; l >= 0; --l) {
         STMGCN_REQUIRE(wpt[l] && dbp[l], STMGCN_ERR_ARG, "lstm_step_bwd: wpt/dbp[%d] null", l);
@@ -342,13 +345,16 @@ int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
         const bool l0 = (l == 0);
         if (wimg_t && wimg_t[l] && hid == 64 && (!l0 || c_in <= lstm_tc_max_c_bwd()) && aligned16(g_lt)) {
             // tcgen05 path: pointwise + data GEMM fused in one kernel (lstm_tc.cu)
-            int32_t rc = launch_lstm_bwd_tc(l0 ? 64 : 128, g_lt, c_t, c_prev, dh_in, dh_rec + (int64_t)l * rh,
-                                            dc + (int64_t)l * rh, l0 ? nullptr : dx_work, wimg_t[l], dbp[l],
+            int32_t rc = launch_lstm_bwd_tc(l0 ? 64 : 128, g_lt, c_t, c_prev, dh_in, dh_rec + (int64_t)l * ws_rh,
+                                            dc + (int64_t)l * ws_rh, l0 ? nullptr : dx_work, wimg_t[l], dbp[l],
                                             l0 ? wx : nullptr, l0 ? dwx : nullptr, xo, s_gate, d_s, c_in, t, t_len,
-                                            b_inner, rows, st);
+                                            b_inner, rows, blocked_ws, st);
             if (rc) return rc;
             continue;
         }
+        STMGCN_REQUIRE(!blocked_ws, STMGCN_ERR_STATE,
+                       "lstm_step_bwd: tile-blocked workspaces need the tensor-core kernels on every layer (layer %d falls "
+                       "back to the FFMA kernels)", l);
         size_t smem = (size_t)h4 * (1 + (l0 ? c_in : 0)) * sizeof(float);
         if (l0 && b_inner <= 2048) smem += (size_t)b_inner * sizeof(float);
         lstm_bwd_pointwise_kernel<<<grid_pw, 256, smem, st>>>(

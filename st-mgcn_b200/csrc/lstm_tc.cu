@@ -287,7 +287,14 @@ struct BwdParams {
     int64_t rows;
     int n_tiles;
     int prefetch;
+    int blocked;             // dh_in / dh_rec / dc / dx_out use the tile-blocked layout [tile][unit/8][128 rows][8 units]
 };
+
+// element (row r, unit u) of a (rows x 64) workspace: row-major or tile-blocked (each 8-unit k-block slice of a
+// 128-row tile is one contiguous 4 KB run, so the loader's reads and the epilogue's writes are full lines)
+__device__ __forceinline__ int64_t ws_off(int blocked, int64_t r, int unit) {
+    return blocked ? ((((r >> 7) * 8 + (unit >> 3)) * kTileM + (r & 127)) * 8 + (unit & 7)) : r * kHid + unit;
+}
 
 template <int N>
 __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __grid_constant__ BwdParams p) {
@@ -358,11 +365,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
                     if (r < p.rows) {
                         const int64_t e = r * kHid + unit;
                         buf[i].g = *reinterpret_cast<const float4*>(p.gates + r * kGateCols + 4 * unit);
-                        buf[i].dh = p.dh_rec[e];
-                        if (p.dh_in) buf[i].dh2 = p.dh_in[e];
+                        const int64_t eb = ws_off(p.blocked, r, unit);
+                        buf[i].dh = p.dh_rec[eb];
+                        if (p.dh_in) buf[i].dh2 = p.dh_in[eb];
                         buf[i].ct = p.c_t[e];
                         buf[i].cp = p.c_prev ? p.c_prev[e] : 0.f;
-                        buf[i].dc = p.dc[e];
+                        buf[i].dc = p.dc[eb];
                     }
                 }
             }
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
             for (int i = 0; i < kCells; ++i) {
                 const int64_t r = row_base + rsub + kRowStep * i;
                 if (r < p.rows) {
-                    p.dc[r * kHid + unit] = dcn[i];
+                    p.dc[ws_off(p.blocked, r, unit)] = dcn[i];
                     *reinterpret_cast<float4*>(p.gates + r * kGateCols + 4 * unit) = da[i];
                 }
             }
@@ -494,11 +502,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
                 if (valid) {
                     // columns [0,64) of a 128-wide result are dx_below, the last 64 are dh_prev
                     const int col = chunk * 32;
-                    float* dst = (N == 128 && col < 64) ? p.dx_out + r * kHid + col
-                                                        : p.dh_rec + r * kHid + (col - (N == 128 ? 64 : 0));
+                    float* base = (N == 128 && col < 64) ? p.dx_out : p.dh_rec;
+                    const int unit0 = col - ((N == 128 && col >= 64) ? 64 : 0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<uint4*>(dst + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(base + ws_off(p.blocked, r, unit0 + 4 * j)) =
+                            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
             }
             tc_fence_before();
@@ -772,7 +781,7 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
 int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* c_prev, const float* dh_in,
                            float* dh_rec, float* dc, float* dx_out, const float* wimg_t, float* dbp, const float* wx,
                            float* dwx, const float* xo, const float* sg, float* d_s, int c_in, int t, int t_len,
-                           int64_t b_inner, int64_t rows, cudaStream_t st) {
+                           int64_t b_inner, int64_t rows, int blocked, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         STMGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -803,6 +812,7 @@ int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* 
     p.rows = rows;
     p.n_tiles = (int)ceil_div(rows, kTileM);
     p.prefetch = tc_prefetch_enabled();
+    p.blocked = blocked;
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
     if (kd == 128)
         lstm_bwd_tc_kernel<128><<<grid, kBwdThreads, BwdCfg<128>::kSmem, st>>>(p);

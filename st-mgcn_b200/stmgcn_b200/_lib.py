@@ -43,7 +43,7 @@ SIGNATURES = [
     ("stmgcn_lstm_pack_tc", c_int32, [_P, c_int32, _P, c_int32, c_int32, _P, _P, _P]),
     ("stmgcn_lstm_step_bwd", c_int32, [c_int32, c_int32, c_int32, c_int64, c_int32, c_int32, c_int64, _P, _P,
                                        _P, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                                       POINTER(c_void_p), _P]),
+                                       POINTER(c_void_p), c_int32, _P]),
     ("stmgcn_lstm_wgrad", c_int32, [c_int32, c_int32, c_int32, c_int64, c_int32, _P, _P, _P, _P, c_int32, _P]),
     ("stmgcn_fuse_out_fwd", c_int32, [POINTER(c_void_p), c_int32, c_int64, c_int64, c_int32, c_int32, _P, _P,
                                       _P, _P, _P]),

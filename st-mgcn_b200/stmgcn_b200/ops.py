@@ -360,9 +360,17 @@ class SharedLSTM(torch.autograd.Function):
         rows = n * b
         dev = xo.device
         d_top = _f32c(d_top).view(rows, hid)
-        dh_rec = torch.zeros((n_layers, rows, hid), device=dev, dtype=torch.float32)
-        dc = torch.zeros((n_layers, rows, hid), device=dev, dtype=torch.float32)
-        dx_work = torch.empty((rows, hid), device=dev, dtype=torch.float32)
+        # tensor-core kernels on every layer (input_dim == 1): tile-blocked workspaces, every 8-unit slice of a 128-row
+        # tile is one contiguous 4 KB run (full-line loads/stores instead of 32-byte pieces at a 256-byte stride)
+        blocked = bool(ctx.tc and c_in == 1 and os.environ.get("STMGCN_BLOCKED_WS", "1") != "0")
+        rows_ws = ((rows + 127) // 128) * 128 if blocked else rows
+        if blocked:
+            pad = torch.zeros((rows_ws, hid), device=dev, dtype=torch.float32)
+            pad[:rows] = d_top
+            d_top = pad.view(rows_ws // 128, 128, 8, 8).permute(0, 2, 1, 3).contiguous()
+        dh_rec = torch.zeros((n_layers, rows_ws, hid), device=dev, dtype=torch.float32)
+        dc = torch.zeros((n_layers, rows_ws, hid), device=dev, dtype=torch.float32)
+        dx_work = torch.empty((rows_ws, hid), device=dev, dtype=torch.float32)
         d_s = torch.zeros((b, t_len), device=dev, dtype=torch.float32)
         dwx = torch.zeros_like(wx)
         dbp = [torch.zeros(4 * hid, device=dev, dtype=torch.float32) for _ in range(n_layers)]
@@ -376,7 +384,7 @@ class SharedLSTM(torch.autograd.Function):
                                               s_gate.data_ptr(), wx.data_ptr(), wpt_arr, wimg_t_arr, _p(c0), cs.data_ptr(),
                                               gates.data_ptr(), d_top.data_ptr(), dh_rec.data_ptr(),
                                               dc.data_ptr(), dx_work.data_ptr(), d_s.data_ptr(), dwx.data_ptr(),
-                                              dbp_arr, st), "lstm_step_bwd")
+                                              dbp_arr, int(blocked), st), "lstm_step_bwd")
         for l in range(n_layers):
             _lib.check(L.stmgcn_lstm_wgrad(l, t_len, n_layers, rows, hid, _p(h0), hs.data_ptr(), gates.data_ptr(),
                                            dwp[l].data_ptr(), int(ctx.tc), st), "lstm_wgrad")
