@@ -125,12 +125,14 @@ int32_t stmgcn_gate_bwd(const float* d_s, const float* z, const float* a1, const
  * xo: (R, T, C) node-major observations, s_gate: (B, T) context gate (the modulation xo * s is fused into
  * the layer-0 input read, STMGCN.py:44).  h0/c0: (L, R, H) or NULL (zeros, STMGCN.py:53-57).
  * wimg: optional per-layer tensor-core weight images (see stmgcn_lstm_pack_tc) or NULL.
+ * blocked_cs != 0 (tensor-core kernels on every layer only): cs and c0 are tile-blocked like the backward
+ * workspaces (see stmgcn_lstm_step_bwd), ceil(R/128)*128 rows per (layer, step) slice; hs stays row-major.
  * Step t computes layers 0..L-1.  Limits: H % 4 == 0, H <= 128, C <= 4, L <= 8. */
 int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
                              const float* wx, const float* const* wp, const float* const* bp,
                              const float* const* wimg, const float* h0, const float* c0, float* hs, float* cs,
-                             float* gates, void* stream);
+                             float* gates, int32_t blocked_cs, void* stream);
 /* Tensor-core operand images of one packed layer (H = 64 only): 32-wide k-blocks of [hi | lo] K-major
  * 128B-swizzled fp32 tiles holding the tf32 hi / lo split of the weights (3xTF32 scheme).
  *   img_fwd (kd_fwd*256*2 floats) from wp_fwd (kd_fwd, 4H): operand of gates = A . Wp (tiles [256][32]).
@@ -147,7 +149,7 @@ int32_t stmgcn_lstm_pack_tc(const float* wp_fwd, int32_t kd_fwd, const float* wp
  * Workspaces, zeroed by the caller before t = T-1: dh_rec, dc: (L, R, H); dx_work: (R, H).
  * gates[l][t] is overwritten IN PLACE with the pre-activation gradients dA (stmgcn_lstm_wgrad reads them).
  * wimg_t: optional per-layer tensor-core images of Wp^T (stmgcn_lstm_pack_tc) or NULL.
- * blocked_ws != 0 (tensor-core kernels on every layer only): d_top, dh_rec, dc, dx_work are tile-blocked,
+ * blocked_ws != 0 (tensor-core kernels on every layer only): d_top, dh_rec, dc, dx_work AND cs / c0 are tile-blocked,
  * element (r, u) at (((r/128)*8 + u/8)*128 + r%128)*8 + u%8, with ceil(R/128)*128 rows per (layer) slice.
  * Accumulates (+=; caller zeroes): d_s (B,T) = sum_{n,c} dxmod * xo (gate adjoint, STMGCN.py:44),
  * dwx (C,4H), dbp[l] (4H). */

@@ -15,7 +15,7 @@ namespace stmgcn {
 int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int aux, const float* wimg, const float* bias,
                             const float* xo, const float* sg, int c_in, int t, int t_len, int64_t b_inner,
                             const float* c_prev, float* h_out, float* c_out, float* gates_out, int64_t rows,
-                            cudaStream_t st);
+                            int blocked_cs, cudaStream_t st);
 int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* c_prev, const float* dh_in,
                            float* dh_rec, float* dc, float* dx_out, const float* wimg_t, float* dbp, const float* wx,
                            float* dwx, const float* xo, const float* sg, float* d_s, int c_in, int t, int t_len,
@@ -264,16 +264,17 @@ int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
                              const float* wx, const float* const* wp, const float* const* bp,
                              const float* const* wimg, const float* h0, const float* c0, float* hs, float* cs,
-                             float* gates, void* stream) {
+                             float* gates, int32_t blocked_cs, void* stream) {
     STMGCN_REQUIRE(xo && s_gate && wx && wp && bp && hs && cs, STMGCN_ERR_ARG, "lstm_step_fwd: null pointer");
     if (int32_t rc = check_dims("lstm_step_fwd", t, t_len, n_layers, rows, hid, c_in, b_inner)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t rh = rows * hid;
+    const int64_t crh = blocked_cs ? ceil_div(rows, 128) * 128 * hid : rh;     // cs / c0 slice size (padded when blocked)
     const int h4 = 4 * hid;
     for (int l = 0; l < n_layers; ++l) {
         STMGCN_REQUIRE(wp[l] && bp[l], STMGCN_ERR_ARG, "lstm_step_fwd: wp/bp[%d] null", l);
         const float* h_prev = t > 0 ? hs + ((int64_t)(l * t_len + t - 1)) * rh : (h0 ? h0 + (int64_t)l * rh : nullptr);
-        const float* c_prev = t > 0 ? cs + ((int64_t)(l * t_len + t - 1)) * rh : (c0 ? c0 + (int64_t)l * rh : nullptr);
+        const float* c_prev = t > 0 ? cs + ((int64_t)(l * t_len + t - 1)) * crh : (c0 ? c0 + (int64_t)l * crh : nullptr);
         ASegs a{};
         a.segw = hid;
         a.lda = hid;
@@ -296,7 +297,7 @@ int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
         epi.b_inner = b_inner;
         epi.c_prev = c_prev;
         epi.h_out = hs + ((int64_t)(l * t_len + t)) * rh;
-        epi.c_out = cs + ((int64_t)(l * t_len + t)) * rh;
+        epi.c_out = cs + ((int64_t)(l * t_len + t)) * crh;
         epi.gates_out = gates ? gates + ((int64_t)(l * t_len + t)) * rows * h4 : nullptr;
         epi.hid = hid;
         epi.half_units = 256 / 8;
@@ -308,10 +309,12 @@ int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
         if (tc_ok) {   // tcgen05 3xTF32 path (lstm_tc.cu)
             rc = launch_lstm_cell_tc(a.seg[0], a.nseg > 1 ? a.seg[1] : nullptr, a.nseg, l == 0 ? 1 : 0, wimg[l], bp[l], xo,
                                      s_gate, c_in, t, t_len, b_inner, c_prev, epi.h_out, epi.c_out, epi.gates_out,
-                                     rows, st);
+                                     rows, blocked_cs, st);
             if (rc) return rc;
             continue;
         }
+        STMGCN_REQUIRE(!blocked_cs, STMGCN_ERR_STATE,
+                       "lstm_step_fwd: a tile-blocked cell-state tape needs the tensor-core kernel on every layer (layer %d)", l);
         if (vec_ok(a, wp[l], h4, h4))
             rc = launch_tall<256, true>(a, rows, kd, wp[l], h4, h4, epi, st, "lstm_step_fwd");
         else
@@ -339,8 +342,8 @@ int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
     for (int l = n_layers - 1; l >= 0; --l) {
         STMGCN_REQUIRE(wpt[l] && dbp[l], STMGCN_ERR_ARG, "lstm_step_bwd: wpt/dbp[%d] null", l);
         float* g_lt = gates + ((int64_t)(l * t_len + t)) * rows * h4;
-        const float* c_t = cs + ((int64_t)(l * t_len + t)) * rh;
-        const float* c_prev = t > 0 ? cs + ((int64_t)(l * t_len + t - 1)) * rh : (c0 ? c0 + (int64_t)l * rh : nullptr);
+        const float* c_t = cs + ((int64_t)(l * t_len + t)) * ws_rh;
+        const float* c_prev = t > 0 ? cs + ((int64_t)(l * t_len + t - 1)) * ws_rh : (c0 ? c0 + (int64_t)l * ws_rh : nullptr);
         const float* dh_in = (l == n_layers - 1) ? ((t == t_len - 1) ? d_top : nullptr) : dx_work;
         const bool l0 = (l == 0);
         if (wimg_t && wimg_t[l] && hid == 64 && (!l0 || c_in <= lstm_tc_max_c_bwd()) && aligned16(g_lt)) {

@@ -26,6 +26,13 @@ namespace {
 constexpr int kNumLoaders = 512;     // 16 loader warps (backward): the loaders are latency-bound, TLP is what helps
 constexpr int kLoaderWarps = kNumLoaders / 32;
 
+// element (row r, unit u) of a (rows x 64) workspace: row-major or tile-blocked (each 8-unit k-block slice of a
+// 128-row tile is one contiguous 4 KB run, so the loader's reads and the epilogue's writes are full lines)
+__device__ __forceinline__ int64_t ws_off(int blocked, int64_t r, int unit) {
+    return blocked ? ((((r >> 7) * 8 + (unit >> 3)) * kTileM + (r & 127)) * 8 + (unit & 7)) : r * kHid + unit;
+}
+
+
 // =====================================================================================================
 // forward cell
 // =====================================================================================================
@@ -64,6 +71,7 @@ struct CellParams {
     float* gates_out;        // (rows,256) or nullptr
     int64_t rows;
     int n_tiles;
+    int blocked_cs;          // c_prev / c_out use the tile-blocked layout (see ws_off)
     int prefetch;            // bulk L2 prefetch of the next tile's inputs (STMGCN_TC_PREFETCH=1; default off)
 };
 
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                     const uint32_t bh = (uint32_t)(nr * kHid * 4);
                     if (p.seg0) prefetch_l2(p.seg0 + r0 * kHid, bh);
                     if (p.seg1) prefetch_l2(p.seg1 + r0 * kHid, bh);
-                    if (p.c_prev) prefetch_l2(p.c_prev + r0 * kHid, bh);
+                    if (p.c_prev) prefetch_l2(p.c_prev + r0 * kHid, bh);     // (a 128-row tile is contiguous in both layouts)
                 }
             }
         }
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
             for (int j = 0; j < 4; ++j) {
                 cpv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.c_prev != nullptr && valid)
-                    cpv[j] = *reinterpret_cast<const float4*>(p.c_prev + r * kHid + part * 16 + 4 * j);
+                    cpv[j] = *reinterpret_cast<const float4*>(p.c_prev + ws_off(p.blocked_cs, r, part * 16 + 4 * j));
             }
             mbar_wait(&bar->tmem_full[a], aph, 3);
             tc_fence_after();
@@ -211,7 +219,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                 }
                 if (valid) {
                     *reinterpret_cast<float4*>(p.h_out + r * kHid + unit0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    *reinterpret_cast<float4*>(p.c_out + r * kHid + unit0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    *reinterpret_cast<float4*>(p.c_out + ws_off(p.blocked_cs, r, unit0)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                 }
                 if (p.gates_out != nullptr) {
                     // gate tape: transpose through this warp's [32][16] staging tile so a store instruction writes
@@ -290,12 +298,6 @@ struct BwdParams {
     int blocked;             // dh_in / dh_rec / dc / dx_out use the tile-blocked layout [tile][unit/8][128 rows][8 units]
 };
 
-// element (row r, unit u) of a (rows x 64) workspace: row-major or tile-blocked (each 8-unit k-block slice of a
-// 128-row tile is one contiguous 4 KB run, so the loader's reads and the epilogue's writes are full lines)
-__device__ __forceinline__ int64_t ws_off(int blocked, int64_t r, int unit) {
-    return blocked ? ((((r >> 7) * 8 + (unit >> 3)) * kTileM + (r & 127)) * 8 + (unit & 7)) : r * kHid + unit;
-}
-
 template <int N>
 __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __grid_constant__ BwdParams p) {
     using Cfg = BwdCfg<N>;
@@ -368,8 +370,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
                         const int64_t eb = ws_off(p.blocked, r, unit);
                         buf[i].dh = p.dh_rec[eb];
                         if (p.dh_in) buf[i].dh2 = p.dh_in[eb];
-                        buf[i].ct = p.c_t[e];
-                        buf[i].cp = p.c_prev ? p.c_prev[e] : 0.f;
+                        buf[i].ct = p.c_t[eb];                      // the cell-state tape shares the workspace layout
+                        buf[i].cp = p.c_prev ? p.c_prev[eb] : 0.f;
                         buf[i].dc = p.dc[eb];
                     }
                 }
@@ -745,7 +747,7 @@ static int tc_prefetch_enabled() {
 int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int aux, const float* wimg, const float* bias,
                             const float* xo, const float* sg, int c_in, int t, int t_len, int64_t b_inner,
                             const float* c_prev, float* h_out, float* c_out, float* gates_out, int64_t rows,
-                            cudaStream_t st) {
+                            int blocked_cs, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
         STMGCN_CUDA(cudaFuncSetAttribute(lstm_cell_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
@@ -770,6 +772,7 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
     p.gates_out = gates_out;
     p.rows = rows;
     p.n_tiles = (int)ceil_div(rows, kTileM);
+    p.blocked_cs = blocked_cs;
     p.prefetch = tc_prefetch_enabled();
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
     lstm_cell_tc_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(p);

@@ -39,7 +39,7 @@ SIGNATURES = [
     ("stmgcn_gate_bwd", c_int32, [_P, _P, _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P]),
     ("stmgcn_lstm_step_fwd", c_int32, [c_int32, c_int32, c_int32, c_int64, c_int32, c_int32, c_int64, _P, _P,
                                        _P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P,
-                                       _P, _P]),
+                                       _P, c_int32, _P]),
     ("stmgcn_lstm_pack_tc", c_int32, [_P, c_int32, _P, c_int32, c_int32, _P, _P, _P]),
     ("stmgcn_lstm_step_bwd", c_int32, [c_int32, c_int32, c_int32, c_int64, c_int32, c_int32, c_int64, _P, _P,
                                        _P, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _P,

@@ -91,7 +91,7 @@ class CG_LSTM(nn.Module):
                    getattr(self.lstm, f"bias_ih_l{l}"), getattr(self.lstm, f"bias_hh_l{l}")]
         return ws
 
-    def forward_node_major(self, sset, xo: torch.Tensor, xt: torch.Tensor, h0=None, c0=None):
+    def forward_node_major(self, sset, xo: torch.Tensor, xt: torch.Tensor, h0=None, c0=None, want_state: bool = False):
         """xo (N,B,T,C), xt (N,B,T) node-major -> (h_top (N,B,H), h_n, c_n (L, N*B, H))."""
         gc = self.gconv_temporal_feats
         n = xt.shape[0]
@@ -101,7 +101,7 @@ class CG_LSTM(nn.Module):
         else:       # exotic activation class: kernel does the GCN, torch applies the module + pooling
             pool = (xt + gc.forward_node_major(sset, xt)).sum(dim=0)
         s = ops.ContextGate.apply(pool, self.fc.weight, self.fc.bias, n)
-        return ops.SharedLSTM.apply(xo, s, h0, c0, self.lstm_num_layers, self.lstm_hidden_dim,
+        return ops.SharedLSTM.apply(xo, s, h0, c0, self.lstm_num_layers, self.lstm_hidden_dim, want_state,
                                     *self._lstm_weights())
 
     def forward(self, adj, obs_seq: torch.Tensor, hidden: tuple):
@@ -115,7 +115,7 @@ class CG_LSTM(nn.Module):
             # reference rows are b*N + n (STMGCN.py:47); kernels use n*B + b
             h0 = hidden[0].reshape(lyr, b, n, hid).permute(0, 2, 1, 3).reshape(lyr, n * b, hid)
             c0 = hidden[1].reshape(lyr, b, n, hid).permute(0, 2, 1, 3).reshape(lyr, n * b, hid)
-        h_top, h_n, c_n = self.forward_node_major(sset, xo, xt, h0, c0)
+        h_top, h_n, c_n = self.forward_node_major(sset, xo, xt, h0, c0, want_state=True)
         to_ref = lambda v: v.reshape(lyr, n, b, hid).permute(0, 2, 1, 3).reshape(lyr, b * n, hid)
         return h_top.permute(1, 0, 2), (to_ref(h_n), to_ref(c_n))
 

@@ -266,6 +266,23 @@ class ContextGate(torch.autograd.Function):
         return d_z / float(ctx.n_regions), d_fcw, d_fcb, None
 
 
+def to_blocked(x: torch.Tensor) -> torch.Tensor:
+    """(..., R, 64) row-major -> tile-blocked (..., ceil(R/128)*128, 64) flat layout [tile][unit/8][128][8]."""
+    *lead, r, h = x.shape
+    rp = ((r + 127) // 128) * 128
+    if rp != r:
+        pad = x.new_zeros(*lead, rp, h)
+        pad[..., :r, :] = x
+        x = pad
+    return x.reshape(*lead, rp // 128, 128, 8, 8).transpose(-3, -2).contiguous().reshape(*lead, rp, h)
+
+
+def from_blocked(x: torch.Tensor, rows: int) -> torch.Tensor:
+    """Inverse of :func:`to_blocked`."""
+    *lead, rp, h = x.shape
+    return x.reshape(*lead, rp // 128, 8, 128, 8).transpose(-3, -2).reshape(*lead, rp, h)[..., :rows, :].contiguous()
+
+
 def _pack_lstm(weights: Sequence[torch.Tensor], n_layers: int, hid: int):
     """nn.LSTM parameters -> packed operands (see include/stmgcn_b200.h)."""
     w_ih0 = weights[0]
@@ -301,13 +318,13 @@ def _unpack_lstm_grads(dwx, dwp, dbp, n_layers: int, hid: int, c_in: int):
 class SharedLSTM(torch.autograd.Function):
     """h_top (N,B,H) of the shared multi-layer LSTM over rows r = n*B + b; input ``xo * s[b,t]``.
 
-    forward(xo (N,B,T,C), s (B,T), h0|None, c0|None (L,R,H), n_layers, hid, *lstm_weights) where
+    forward(xo (N,B,T,C), s (B,T), h0|None, c0|None (L,R,H), n_layers, hid, want_state, *lstm_weights) where
     lstm_weights = [w_ih_l0, w_hh_l0, b_ih_l0, b_hh_l0, w_ih_l1, ...] (nn.LSTM names/shapes).
     Returns (h_top, h_n (L,R,H), c_n (L,R,H)); the last two are not differentiable.
     """
 
     @staticmethod
-    def forward(ctx, xo, s_gate, h0, c0, n_layers: int, hid: int, *weights):
+    def forward(ctx, xo, s_gate, h0, c0, n_layers: int, hid: int, want_state: bool, *weights):
         _require_cuda(xo, s_gate, *weights)
         xo, s_gate = _f32c(xo), _f32c(s_gate)
         weights = [_f32c(w) for w in weights]
@@ -318,8 +335,14 @@ class SharedLSTM(torch.autograd.Function):
         c0c = _f32c(c0) if c0 is not None else None
         need_grad = any(ctx.needs_input_grad)
         wx, wp, bp, wpt = _pack_lstm(weights, n_layers, hid)
+        # tensor-core kernels on every layer (H = 64, input_dim = 1): the cell-state tape and the backward workspaces are
+        # tile-blocked so every 8-unit slice of a 128-row tile is one contiguous 4 KB run (see stmgcn_lstm_step_bwd)
+        blocked = bool(hid == 64 and lstm_path() == "tc" and c_in == 1 and os.environ.get("STMGCN_BLOCKED_WS", "1") != "0")
+        rows_c = ((rows + 127) // 128) * 128 if blocked else rows
+        if blocked and c0c is not None:
+            c0c = to_blocked(c0c)
         hs = torch.empty((n_layers, t_len, rows, hid), device=dev, dtype=torch.float32)
-        cs = torch.empty((n_layers, t_len, rows, hid), device=dev, dtype=torch.float32)
+        cs = torch.empty((n_layers, t_len, rows_c, hid), device=dev, dtype=torch.float32)
         gates = torch.empty((n_layers, t_len, rows, 4 * hid), device=dev, dtype=torch.float32) if need_grad else None
         wp_arr, bp_arr = _lib.ptr_array([w.data_ptr() for w in wp]), _lib.ptr_array([v.data_ptr() for v in bp])
         st = _stream()
@@ -341,13 +364,19 @@ class SharedLSTM(torch.autograd.Function):
         for t in range(t_len):
             _lib.check(L.stmgcn_lstm_step_fwd(t, t_len, n_layers, rows, hid, c_in, b, xo.data_ptr(),
                                               s_gate.data_ptr(), wx.data_ptr(), wp_arr, bp_arr, wimg_arr, _p(h0c),
-                                              _p(c0c), hs.data_ptr(), cs.data_ptr(), _p(gates), st), "lstm_step_fwd")
+                                              _p(c0c), hs.data_ptr(), cs.data_ptr(), _p(gates), int(blocked), st),
+                       "lstm_step_fwd")
         ctx.dims = (n, b, t_len, c_in, n_layers, hid)
         ctx.tc = wimg is not None
+        ctx.blocked = blocked
         if need_grad:
             ctx.save_for_backward(xo, s_gate, h0c, c0c, hs, cs, gates, wx, *wpt, *(wimg_t if ctx.tc else []))
         h_top = hs[n_layers - 1, t_len - 1].view(n, b, hid)
-        h_n, c_n = hs[:, t_len - 1], cs[:, t_len - 1]
+        if want_state:
+            h_n = hs[:, t_len - 1]
+            c_n = from_blocked(cs[:, t_len - 1], rows) if blocked else cs[:, t_len - 1]
+        else:                       # ST_MGCN discards the final state (STMGCN.py:113): skip the layout conversion
+            h_n = c_n = hs.new_empty(0)
         ctx.mark_non_differentiable(h_n, c_n)
         return h_top, h_n, c_n
 
@@ -362,7 +391,7 @@ class SharedLSTM(torch.autograd.Function):
         d_top = _f32c(d_top).view(rows, hid)
         # tensor-core kernels on every layer (input_dim == 1): tile-blocked workspaces, every 8-unit slice of a 128-row
         # tile is one contiguous 4 KB run (full-line loads/stores instead of 32-byte pieces at a 256-byte stride)
-        blocked = bool(ctx.tc and c_in == 1 and os.environ.get("STMGCN_BLOCKED_WS", "1") != "0")
+        blocked = ctx.blocked
         rows_ws = ((rows + 127) // 128) * 128 if blocked else rows
         if blocked:
             pad = torch.zeros((rows_ws, hid), device=dev, dtype=torch.float32)
@@ -389,7 +418,7 @@ class SharedLSTM(torch.autograd.Function):
             _lib.check(L.stmgcn_lstm_wgrad(l, t_len, n_layers, rows, hid, _p(h0), hs.data_ptr(), gates.data_ptr(),
                                            dwp[l].data_ptr(), int(ctx.tc), st), "lstm_wgrad")
         w_grads = _unpack_lstm_grads(dwx, dwp, dbp, n_layers, hid, c_in)
-        return (None, d_s, None, None, None, None, *w_grads)
+        return (None, d_s, None, None, None, None, None, *w_grads)
 
 
 class FuseOut(torch.autograd.Function):

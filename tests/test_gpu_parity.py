@@ -216,7 +216,7 @@ def test_lstm_tensor_core_path_matches_exact_fp32_path(rows_n, b, t, c):
         for path in ("fma", "tc"):
             ops.set_lstm_path(path)
             with torch.no_grad():
-                outs[path] = [v.clone() for v in ops.SharedLSTM.apply(xo, s, h0, c0, lyr, hid, *ws)]
+                outs[path] = [v.clone() for v in ops.SharedLSTM.apply(xo, s, h0, c0, lyr, hid, True, *ws)]
     finally:
         ops.set_lstm_path(old)
     for name, a, b_ in zip(("h_top", "h_n", "c_n"), outs["tc"], outs["fma"]):
@@ -245,7 +245,7 @@ def test_lstm_tensor_core_backward_matches_exact_fp32_path(rows_n, b, t, c):
             ops.set_lstm_path(path)
             s = s0.clone().requires_grad_(True)
             ws = [w.to(DEV).requires_grad_(True) for w in ws0]
-            h_top, _, _ = ops.SharedLSTM.apply(xo, s, None, None, lyr, hid, *ws)
+            h_top, _, _ = ops.SharedLSTM.apply(xo, s, None, None, lyr, hid, False, *ws)
             (h_top * proj).sum().backward()
             res[path] = [s.grad.clone()] + [w.grad.clone() for w in ws]
     finally:
