@@ -146,7 +146,8 @@ int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
 int32_t stmgcn_lstm_pack_tc(const float* wp_fwd, int32_t kd_fwd, const float* wp_bwd, int32_t kd_bwd, int32_t hid,
                             float* img_fwd, float* img_bwd, void* stream);
 /* BPTT step t (call t = T-1 .. 0).  d_top: (R, H) gradient of hs[L-1][T-1] (read at t = T-1 only).
- * Workspaces, zeroed by the caller before t = T-1: dh_rec, dc: (L, R, H); dx_work: (R, H).
+ * Workspaces: dh_rec, dc: (L, R, H); dx_work: (R, H).  No initialisation is needed: the call with t = T-1 treats the
+ * incoming dh_rec / dc as zero without reading them (h_n / c_n carry no gradient, STMGCN.py:113).
  * gates[l][t] is overwritten IN PLACE with the pre-activation gradients dA (stmgcn_lstm_wgrad reads them).
  * wimg_t: optional per-layer tensor-core images of Wp^T (stmgcn_lstm_pack_tc) or NULL.
  * blocked_ws != 0 (tensor-core kernels on every layer only): d_top, dh_rec, dc, dx_work AND cs / c0 are tile-blocked,

@@ -128,6 +128,7 @@ lstm_bwd_pointwise_kernel(int64_t rows, int hid, float* __restrict__ gates, cons
                           const float* __restrict__ wx, float* __restrict__ dwx, const float* __restrict__ xo,
                           const float* __restrict__ sg, float* __restrict__ d_s, int c_in, int t, int t_len,
                           int64_t b_inner) {
+    const bool first = (t == t_len - 1);     // the incoming dh_rec / dc are zero by definition at the last time step
     extern __shared__ float sm[];            // [4H] dbias | [C*4H] dwx | [b_inner] ds (if it fits)
     const int h4 = 4 * hid;
     float* s_db = sm;
@@ -168,11 +169,11 @@ lstm_bwd_pointwise_kernel(int64_t rows, int hid, float* __restrict__ gates, cons
             if (u >= ul || unit >= hid) continue;
             const int64_t e = r * hid + unit;
             const float4 g = *reinterpret_cast<const float4*>(gates + r * h4 + 4 * unit);   // i,f,g,o
-            float dh = dh_rec[e];
+            float dh = first ? 0.f : dh_rec[e];
             if (dh_in) dh += dh_in[e];
             const float tc = tanhf_(c_t[e]);
             const float cp = c_prev ? c_prev[e] : 0.f;
-            const float dcv = dc[e] + dh * g.w * (1.f - tc * tc);
+            const float dcv = (first ? 0.f : dc[e]) + dh * g.w * (1.f - tc * tc);
             float4 da;
             da.x = dcv * g.z * g.x * (1.f - g.x);
             da.y = dcv * cp * g.y * (1.f - g.y);

@@ -394,11 +394,10 @@ class SharedLSTM(torch.autograd.Function):
         blocked = ctx.blocked
         rows_ws = ((rows + 127) // 128) * 128 if blocked else rows
         if blocked:
-            pad = torch.zeros((rows_ws, hid), device=dev, dtype=torch.float32)
-            pad[:rows] = d_top
-            d_top = pad.view(rows_ws // 128, 128, 8, 8).permute(0, 2, 1, 3).contiguous()
-        dh_rec = torch.zeros((n_layers, rows_ws, hid), device=dev, dtype=torch.float32)
-        dc = torch.zeros((n_layers, rows_ws, hid), device=dev, dtype=torch.float32)
+            d_top = to_blocked(d_top)
+        # dh_rec / dc need no initialisation: the step at t = T-1 treats them as zero (stmgcn_lstm_step_bwd)
+        dh_rec = torch.empty((n_layers, rows_ws, hid), device=dev, dtype=torch.float32)
+        dc = torch.empty((n_layers, rows_ws, hid), device=dev, dtype=torch.float32)
         dx_work = torch.empty((rows_ws, hid), device=dev, dtype=torch.float32)
         d_s = torch.zeros((b, t_len), device=dev, dtype=torch.float32)
         dwx = torch.zeros_like(wx)
