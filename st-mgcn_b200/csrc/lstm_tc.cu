@@ -16,7 +16,9 @@
 //                    tcgen05.commit releases operand stages / publishes accumulators
 // Pipelines: operand stages (full/empty mbarriers) and two TMEM accumulators (tmem_full/tmem_empty).
 #include "tc_pipeline.cuh"
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 using namespace stmgcn;
 using namespace stmgcn::tc;
@@ -72,6 +74,8 @@ struct CellParams {
     int n_tiles;
     int blocked_cs;          // c_prev / c_out use the tile-blocked layout (see ws_off)
     int prefetch;            // bulk L2 prefetch of the next tile's inputs (STMGCN_TC_PREFETCH=1; default off)
+    int gates_tma;           // gate tape leaves through TMA tensor stores (gates_map) instead of per-thread stores
+    alignas(64) CUtensorMap gates_map;   // (rows, 256) fp32 slice of the tape, box 32 rows x 16 columns, 64-byte swizzle
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __grid_constant__ CellParams p) {
@@ -216,31 +220,47 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                     v[4 * u + 2] = __float_as_uint(gg);
                     v[4 * u + 3] = __float_as_uint(go);
                 }
-                if (valid) {
-                    *reinterpret_cast<float4*>(p.h_out + r * kHid + unit0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    *reinterpret_cast<float4*>(p.c_out + ws_off(p.blocked_cs, r, unit0)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                }
                 if (p.gates_out != nullptr) {
-                    // gate tape: transpose through this warp's [32][16] staging tile so a store instruction writes
-                    // 8 row segments of 64 contiguous bytes instead of 32 scattered 16-byte pieces
+                    // gate tape: this warp's [32 rows][16 columns] piece goes through its staging tile (16-byte chunks
+                    // XOR-swizzled with (row >> 1) & 3 == the TMA 64-byte swizzle, conflict-free for the lanes)
+                    if (p.gates_tma) {                 // previous piece's tensor store must have read the tile
+                        if (lane == 0) bulk_wait_read0();
+                    }
                     __syncwarp();
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         *reinterpret_cast<uint4*>(stg + lane * 16 + ((u ^ ((lane >> 1) & 3)) << 2)) =
                             make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-                    __syncwarp();
+                    if (p.gates_tma) {
+                        // one TMA tensor store per piece: no per-thread global stores, rows past the end are clipped
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&p.gates_map, smem_u32(stg), 4 * unit0, (int)r0);
+                            bulk_commit_group();
+                        }
+                    } else {
+                        // a store instruction writes 8 row segments of 64 contiguous bytes
+                        __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int row = i * 8 + (lane >> 2), qq = lane & 3;
-                        const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 16 + ((qq ^ ((row >> 1) & 3)) << 2));
-                        if (r0 + row < p.rows)
-                            *reinterpret_cast<uint4*>(p.gates_out + (r0 + row) * kGateCols + 4 * unit0 + qq * 4) = val;
+                        for (int i = 0; i < 4; ++i) {
+                            const int row = i * 8 + (lane >> 2), qq = lane & 3;
+                            const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 16 + ((qq ^ ((row >> 1) & 3)) << 2));
+                            if (r0 + row < p.rows)
+                                *reinterpret_cast<uint4*>(p.gates_out + (r0 + row) * kGateCols + 4 * unit0 + qq * 4) = val;
+                        }
                     }
+                }
+                // h / c after the tape hand-off: the proxy fence above does not have to wait for these stores
+                if (valid) {
+                    *reinterpret_cast<float4*>(p.h_out + r * kHid + unit0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                    *reinterpret_cast<float4*>(p.c_out + ws_off(p.blocked_cs, r, unit0)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                 }
             }
             tc_fence_before();
             mbar_arrive(&bar->tmem_empty[a]);
         }
+        if (p.gates_tma && lane == 0) bulk_wait0();      // shared memory stays valid until the last tensor store is done
         TC_PROF_FLUSH(2, tid == 0)
     }
     tc_fence_before();
@@ -772,6 +792,43 @@ static int tc_prefetch_enabled() {
     return v;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+// (rows, 256) fp32 row-major slice, box = 32 rows x 16 columns, 64-byte shared-memory swizzle
+static bool make_gates_map(CUtensorMap* map, float* base, int64_t rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)kGateCols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kGateCols * sizeof(float)};
+    const cuuint32_t box[2] = {16, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static int gates_tma_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("STMGCN_GATES_TMA");
+        v = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    return v;
+}
+
 // Called from stmgcn_lstm_step_fwd (lstm.cu) when the tensor-core path applies.  aux != 0 (layer 0): the weight image
 // carries a third k-block [W_ih^T ; b ; 0] and the loader feeds [x*s | 1 | 0] so x.W_ih + b comes out of the MMA.
 int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int aux, const float* wimg, const float* bias,
@@ -804,6 +861,9 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
     p.n_tiles = (int)ceil_div(rows, kTileM);
     p.blocked_cs = blocked_cs;
     p.prefetch = tc_prefetch_enabled();
+    p.gates_tma = 0;
+    memset(&p.gates_map, 0, sizeof(p.gates_map));
+    if (gates_out != nullptr && gates_tma_enabled() && make_gates_map(&p.gates_map, gates_out, rows)) p.gates_tma = 1;
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
     STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel, grid, kFwdThreads, kFwdSmem, st, p));
     count_launch();

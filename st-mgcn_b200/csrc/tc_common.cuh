@@ -102,6 +102,16 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) 
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {      // same warp that allocated
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// ---- TMA tensor stores (shared -> global through a CUtensorMap, bulk async-group completion) ----
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(tmap), "r"(smem_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread's bulk groups have finished READING shared memory (the staging tile may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // programmatic dependent launch: the next kernel of the stream may start its prologue (barrier init, TMEM allocation)
 // on SMs this grid has already left; pdl_wait() blocks until the previous grid has completed and flushed its memory
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
