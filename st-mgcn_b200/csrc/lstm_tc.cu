@@ -272,10 +272,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
 // =====================================================================================================
 // backward: pointwise dA in the loader + data GEMM  [dx_below | dh_prev] = dA . Wp^T
 // =====================================================================================================
-constexpr int kBwdStages = 3;
 constexpr int kBwdEpiWarps = 4;
-constexpr int kBwdThreads = (kBwdEpiWarps + kLoaderWarps + 1) * 32;   // 416
 constexpr int kBwdNkb = kGateCols / kKB;                          // 8
+// TMA-fed variant: a producer thread streams every (tile, k-block) item -- the gate slice through a tensor map, the
+// five tile-blocked (128 x 8) vectors as 4 KB bulk copies -- into one raw slot per loader group, one item ahead of the
+// group's arithmetic.  Bulk copies are tracked by mbarriers, not by the thread's scoreboard, so (unlike register
+// prefetches) they are not waited for by the MEMBAR that fence.proxy.async implies.
+constexpr int kRawGates = kTileM * kKB * 4;                       // 16 KB  [128 rows][32 gate columns]
+constexpr int kRawVec = kTileM * 8 * 4;                           // 4 KB   [128 rows][8 units]
+constexpr int kRawSlot = kRawGates + 5 * kRawVec;                 // 36 KB: gates | dh_rec | dh_in | c_t | c_prev | dc
+constexpr int kRawSlots = 2;                                      // one per loader group
 constexpr int kBwdMaxC = 1;                                       // layer-0 TC backward handles input_dim 1
 
 template <int N>
@@ -284,14 +290,21 @@ struct BwdTailT {
     float s_dwx[N == 64 ? kLoaderWarps : 1][kGateCols];         // layer 0 only (input_dim == 1)
     float s_ds[N == 64 ? 2048 : 1];                             // layer 0 only
     Barriers bar;
+    uint64_t raw_full[kRawSlots];
+    uint64_t raw_empty[kRawSlots];
 };
-template <int N>
+template <int N, bool TMA>
 struct BwdCfg {
     using BwdTail = BwdTailT<N>;
+    static constexpr int kStages = TMA ? 2 : 3;
+    static constexpr int kWarps = kBwdEpiWarps + kLoaderWarps + 1 + (TMA ? 1 : 0);     // + the producer warp
+    static constexpr int kThreads = kWarps * 32;
     static constexpr int kBBytes = N * kKB * 4;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-    static constexpr size_t kSmem = 1024 + (size_t)kBwdStages * kStageBytes + sizeof(BwdTail);
+    static constexpr size_t kRawBytes = TMA ? (size_t)kRawSlots * kRawSlot : 0;
+    static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + kRawBytes + sizeof(BwdTail);
     static constexpr int kTmemCols = 2 * N;      // 256 or 128 (power of two >= 32)
+    static_assert(kSmem <= 232448, "backward kernel exceeds the 227 KB shared-memory limit");
 };
 
 struct BwdParams {
@@ -316,15 +329,19 @@ struct BwdParams {
     int prefetch;
     int blocked;             // dh_in / dh_rec / dc / dx_out use the tile-blocked layout [tile][unit/8][128 rows][8 units]
     int first;               // t == T-1: the incoming dh_rec / dc are zero by definition and are not read
+    alignas(64) CUtensorMap gates_map;   // TMA-fed variant: (rows, 256) slice, box 128 rows x 32 columns, no swizzle
 };
 
-template <int N>
-__global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __grid_constant__ BwdParams p) {
-    using Cfg = BwdCfg<N>;
+template <int N, bool TMA>
+__global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_kernel(const __grid_constant__ BwdParams p) {
+    using Cfg = BwdCfg<N, TMA>;
+    constexpr int kBwdStages = Cfg::kStages;
+    constexpr int kBwdThreads = Cfg::kThreads;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     using BwdTail = typename Cfg::BwdTail;
-    BwdTail* tail = (BwdTail*)(smem + (size_t)kBwdStages * Cfg::kStageBytes);
+    uint8_t* raw = smem + (size_t)kBwdStages * Cfg::kStageBytes;
+    BwdTail* tail = (BwdTail*)(raw + Cfg::kRawBytes);
     Barriers* bar = &tail->bar;
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -334,7 +351,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
     const bool ds_smem = l0 && p.b_inner <= 2048;
 
     pdl_launch_dependents();
-    if (tid == 0) init_barriers(bar, kBwdStages, kBwdEpiWarps * 32, kNumLoaders / 2);     // one loader group per k-block
+    if (tid == 0) {
+        if (TMA)
+            for (int s = 0; s < kRawSlots; ++s) {
+                mbar_init(&tail->raw_full[s], 1);                   // the producer's arrive.expect_tx
+                mbar_init(&tail->raw_empty[s], kNumLoaders / 2);    // every thread of the slot's loader group
+            }
+        init_barriers(bar, kBwdStages, kBwdEpiWarps * 32, kNumLoaders / 2);     // one loader group per k-block
+    }
     if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, Cfg::kTmemCols);
     for (int i = tid; i < kLoaderWarps * kGateCols; i += kBwdThreads) {
         (&tail->s_db[0][0])[i] = 0.f;
@@ -381,6 +405,30 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
                         }
                     }
                 }
+                if (TMA) {
+                    // this group's raw slot was filled by the producer warp while the group worked on its previous item
+                    const uint8_t* rs = raw + (size_t)grp * kRawSlot;
+                    mbar_wait(&tail->raw_full[grp], (uint32_t)((j / kGroups) & 1), 1);
+#pragma unroll
+                    for (int i = 0; i < kCells; ++i) {
+                        const int row = rsub + kRowStep * i;
+                        const bool ok = (int64_t)tile * kTileM + row < p.rows;       // padding rows hold garbage
+                        const float* vec = reinterpret_cast<const float*>(rs + kRawGates) + row * 8 + c;
+                        const float4 g = *reinterpret_cast<const float4*>(rs + row * 128 + c * 16);
+                        const float dh = p.first ? 0.f : vec[0];
+                        const float dh2 = p.dh_in ? vec[kRawVec / 4] : 0.f;
+                        const float ct = vec[2 * (kRawVec / 4)];
+                        const float cp = p.c_prev ? vec[3 * (kRawVec / 4)] : 0.f;
+                        const float dcv = p.first ? 0.f : vec[4 * (kRawVec / 4)];
+                        buf[i].g = ok ? g : make_float4(0.f, 0.f, 0.f, 0.f);
+                        buf[i].dh = ok ? dh : 0.f;
+                        buf[i].dh2 = ok ? dh2 : 0.f;
+                        buf[i].ct = ok ? ct : 0.f;
+                        buf[i].cp = ok ? cp : 0.f;
+                        buf[i].dc = ok ? dcv : 0.f;
+                    }
+                    mbar_arrive(&tail->raw_empty[grp]);        // slot may be refilled (item j + 2)
+                } else {
 #pragma unroll
                 for (int i = 0; i < kCells; ++i) {
                     const int64_t r = (int64_t)tile * kTileM + rsub + kRowStep * i;
@@ -395,6 +443,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
                         buf[i].cp = p.c_prev ? p.c_prev[eb] : 0.f;
                         if (!p.first) buf[i].dc = p.dc[eb];
                     }
+                }
                 }
             }
             const int64_t row_base = (int64_t)tile * kTileM;
@@ -504,6 +553,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_tc_kernel(const __gri
         TC_PROF_FLUSH((N == 128 ? 3 : 6), ltid == 0)
     } else if (warp == kMmaWarp) {
         mma_issuer<N, kBwdStages, (N == 128 ? 1 : 2)>(bar, smem, Cfg::kStageBytes, Cfg::kBBytes, kBwdNkb, p.n_tiles, tmem_base, lane);
+    } else if (TMA && warp == kMmaWarp + 1) {
+        // ===================== producer: TMA loads of the raw inputs, one item ahead per loader group =====================
+        if (lane == 0) {
+            const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int total = my_tiles * kBwdNkb;
+            const uint32_t bytes = kRawGates + kRawVec * (1 + (p.c_prev ? 1 : 0) + (p.dh_in ? 1 : 0) + (p.first ? 0 : 2));
+            for (int j = 0; j < total; ++j) {
+                const int slot = j & 1, n = j >> 1;
+                const int tile = blockIdx.x + (j / kBwdNkb) * gridDim.x, kb = j % kBwdNkb;
+                if (n > 0) mbar_wait_raw(&tail->raw_empty[slot], (uint32_t)((n - 1) & 1));
+                uint8_t* rs = raw + (size_t)slot * kRawSlot;
+                uint64_t* fb = &tail->raw_full[slot];
+                mbar_arrive_expect_tx(fb, bytes);
+                tma_load_2d(rs, &p.gates_map, kb * kKB, tile * kTileM, fb);
+                const int64_t off = ((int64_t)tile * 8 + kb) * (kRawVec / 4);      // tile-blocked (128 x 8) slice
+                uint8_t* v = rs + kRawGates;
+                if (!p.first) bulk_g2s(v, p.dh_rec + off, kRawVec, fb);
+                if (p.dh_in) bulk_g2s(v + kRawVec, p.dh_in + off, kRawVec, fb);
+                bulk_g2s(v + 2 * kRawVec, p.c_t + off, kRawVec, fb);
+                if (p.c_prev) bulk_g2s(v + 3 * kRawVec, p.c_prev + off, kRawVec, fb);
+                if (!p.first) bulk_g2s(v + 4 * kRawVec, p.dc + off, kRawVec, fb);
+            }
+        }
     } else {
         // ===================== epilogue: store [dx_below | dh_prev] =====================
         TC_PROF_DECL
@@ -809,23 +881,29 @@ static EncodeTiledFn encode_tiled_fn() {
     }
     return fn;
 }
-// (rows, 256) fp32 row-major slice, box = 32 rows x 16 columns, 64-byte shared-memory swizzle
-static bool make_gates_map(CUtensorMap* map, float* base, int64_t rows) {
+// (rows, 256) fp32 row-major slice of the gate tape, box = box_rows x box_cols
+static bool make_gates_map(CUtensorMap* map, float* base, int64_t rows, int box_cols, int box_rows, CUtensorMapSwizzle swz) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (fn == nullptr) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)kGateCols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)kGateCols * sizeof(float)};
-    const cuuint32_t box[2] = {16, 32};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-static int gates_tma_enabled() {
+static int env_flag(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e == nullptr ? dflt : (e[0] != '0');
+}
+static int gates_tma_enabled() {      // forward: gate tape through TMA tensor stores (STMGCN_GATES_TMA=0 disables)
     static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("STMGCN_GATES_TMA");
-        v = (e == nullptr || e[0] != '0') ? 1 : 0;
-    }
+    if (v < 0) v = env_flag("STMGCN_GATES_TMA", 1);
+    return v;
+}
+static int bwd_tma_enabled() {        // backward: TMA-fed loaders (STMGCN_BWD_TMA=0 selects the register-load variant)
+    static int v = -1;
+    if (v < 0) v = env_flag("STMGCN_BWD_TMA", 1);
     return v;
 }
 
@@ -863,7 +941,8 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
     p.prefetch = tc_prefetch_enabled();
     p.gates_tma = 0;
     memset(&p.gates_map, 0, sizeof(p.gates_map));
-    if (gates_out != nullptr && gates_tma_enabled() && make_gates_map(&p.gates_map, gates_out, rows)) p.gates_tma = 1;
+    if (gates_out != nullptr && gates_tma_enabled() && make_gates_map(&p.gates_map, gates_out, rows, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B))
+        p.gates_tma = 1;
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
     STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel, grid, kFwdThreads, kFwdSmem, st, p));
     count_launch();
@@ -877,10 +956,14 @@ int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* 
                            int64_t b_inner, int64_t rows, int blocked, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        STMGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)BwdCfg<128>::kSmem));
-        STMGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)BwdCfg<64>::kSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)BwdCfg<128, false>::kSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)BwdCfg<64, false>::kSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)BwdCfg<128, true>::kSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)BwdCfg<64, true>::kSmem));
         attr_done = true;
     }
     BwdParams p;
@@ -908,10 +991,16 @@ int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* 
     p.blocked = blocked;
     p.first = (t == t_len - 1);
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-    if (kd == 128)
-        STMGCN_CUDA(launch_pdl(lstm_bwd_tc_kernel<128>, grid, kBwdThreads, BwdCfg<128>::kSmem, st, p));
-    else
-        STMGCN_CUDA(launch_pdl(lstm_bwd_tc_kernel<64>, grid, kBwdThreads, BwdCfg<64>::kSmem, st, p));
+    // TMA-fed loaders need the tile-blocked workspaces (contiguous 4 KB slices) and a tensor map of the gate slice
+    memset(&p.gates_map, 0, sizeof(p.gates_map));
+    const bool tma = blocked && bwd_tma_enabled() && make_gates_map(&p.gates_map, gates, rows, kKB, kTileM, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (kd == 128) {
+        if (tma) STMGCN_CUDA(launch_pdl(lstm_bwd_tc_kernel<128, true>, grid, BwdCfg<128, true>::kThreads, BwdCfg<128, true>::kSmem, st, p));
+        else STMGCN_CUDA(launch_pdl(lstm_bwd_tc_kernel<128, false>, grid, BwdCfg<128, false>::kThreads, BwdCfg<128, false>::kSmem, st, p));
+    } else {
+        if (tma) STMGCN_CUDA(launch_pdl(lstm_bwd_tc_kernel<64, true>, grid, BwdCfg<64, true>::kThreads, BwdCfg<64, true>::kSmem, st, p));
+        else STMGCN_CUDA(launch_pdl(lstm_bwd_tc_kernel<64, false>, grid, BwdCfg<64, false>::kThreads, BwdCfg<64, false>::kSmem, st, p));
+    }
     count_launch();
     return check_launch("lstm_bwd_tc");
 }

@@ -107,6 +107,11 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_add
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  :: "l"(tmap), "r"(smem_addr), "r"(c0), "r"(c1) : "memory");
 }
+// TMA tensor load (global -> shared through a CUtensorMap), completion (bytes) on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the issuing thread's bulk groups have finished READING shared memory (the staging tile may be overwritten)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
