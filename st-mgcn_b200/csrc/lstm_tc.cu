@@ -280,15 +280,19 @@ constexpr int kBwdNkb = kGateCols / kKB;                          // 8
 // prefetches) they are not waited for by the MEMBAR that fence.proxy.async implies.
 constexpr int kRawGates = kTileM * kKB * 4;                       // 16 KB  [128 rows][32 gate columns]
 constexpr int kRawVec = kTileM * 8 * 4;                           // 4 KB   [128 rows][8 units]
-constexpr int kRawSlot = kRawGates + 5 * kRawVec;                 // 36 KB: gates | dh_rec | dh_in | c_t | c_prev | dc
+constexpr int kRawX = kTileM * 12 * 4;                            // 6 KB   layer 0: the tile's rows of xo (T <= 12, C = 1)
+constexpr int kRawSlot = kRawGates + 5 * kRawVec;                 // 36 KB: gates | dh_rec | dh_in | c_t | c_prev | dc (| x)
 constexpr int kRawSlots = 2;                                      // one per loader group
+constexpr int kBwdSgMax = 1024;                                   // batch entries of the gate / its adjoint kept in smem
 constexpr int kBwdMaxC = 1;                                       // layer-0 TC backward handles input_dim 1
 
 template <int N>
 struct BwdTailT {
     float s_db[kLoaderWarps][kGateCols];                        // per-loader-warp private partial sums
     float s_dwx[N == 64 ? kLoaderWarps : 1][kGateCols];         // layer 0 only (input_dim == 1)
-    float s_ds[N == 64 ? 2048 : 1];                             // layer 0 only
+    float s_ds[N == 64 ? kBwdSgMax : 1];                        // layer 0 only: d s[b, t] partial sums
+    float s_sg[N == 64 ? kBwdSgMax : 1];                        // layer 0 only: s[b, t]
+    float s_wx[N == 64 ? kGateCols : 1];                        // layer 0 only: W_ih row (input_dim == 1)
     Barriers bar;
     uint64_t raw_full[kRawSlots];
     uint64_t raw_empty[kRawSlots];
@@ -301,7 +305,8 @@ struct BwdCfg {
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kBBytes = N * kKB * 4;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-    static constexpr size_t kRawBytes = TMA ? (size_t)kRawSlots * kRawSlot : 0;
+    static constexpr int kSlotBytes = kRawSlot + (N == 64 ? kRawX : 0);
+    static constexpr size_t kRawBytes = TMA ? (size_t)kRawSlots * kSlotBytes : 0;
     static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + kRawBytes + sizeof(BwdTail);
     static constexpr int kTmemCols = 2 * N;      // 256 or 128 (power of two >= 32)
     static_assert(kSmem <= 232448, "backward kernel exceeds the 227 KB shared-memory limit");
@@ -348,7 +353,10 @@ __global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_ker
     const int lane = tid & 31;
     constexpr int kMmaWarp = kBwdEpiWarps + kLoaderWarps;
     constexpr bool l0 = (N == 64);               // layer 0 <=> kd = 64 (no layer below; carries the gate adjoint)
-    const bool ds_smem = l0 && p.b_inner <= 2048;
+    const bool ds_smem = l0 && p.b_inner <= kBwdSgMax;
+    // layer 0, TMA-fed: the tile's xo rows arrive by bulk copy and s[., t] / W_ih sit in shared memory, so the loader
+    // warps issue no global loads at all (any outstanding load would be waited for at the next proxy fence)
+    const bool x_tma = TMA && l0 && ds_smem && p.c_in == 1 && p.t_len * 4 * kTileM <= kRawX && (p.t_len % 4) == 0;
 
     pdl_launch_dependents();
     if (tid == 0) {
@@ -366,6 +374,10 @@ __global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_ker
     }
     if (ds_smem)
         for (int i = tid; i < (int)p.b_inner; i += kBwdThreads) tail->s_ds[i] = 0.f;
+    if (x_tma) {
+        for (int i = tid; i < (int)p.b_inner; i += kBwdThreads) tail->s_sg[i] = p.sg[(int64_t)i * p.t_len + p.t];
+        for (int i = tid; i < kGateCols; i += kBwdThreads) tail->s_wx[i] = p.wx[i];
+    }
     pdl_wait();
     tc_fence_before();
     __syncthreads();
@@ -385,7 +397,7 @@ __global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_ker
         const int grp = ltid / kGT, gtid = ltid % kGT;
         const int c = gtid & 7, rsub = gtid >> 3, lwarp = ltid >> 5;
         struct CellIn { float4 g; float dh, dh2, ct, cp, dc; };
-        float xs[kCells], dxs[kCells];
+        float xs[kCells], dxs[kCells], xraw[kCells];
         const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int total = my_tiles * kBwdNkb;
         for (int j = grp; j < total; j += kGroups) {
@@ -395,8 +407,9 @@ __global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_ker
             {
                 const int unit = kb * 8 + c;
                 if (l0) {
-                    wv = __ldg(reinterpret_cast<const float4*>(p.wx + 4 * unit));
-                    if (kb == grp) {               // this group's first k-block of the tile: modulated inputs of its rows
+                    wv = x_tma ? *reinterpret_cast<const float4*>(&tail->s_wx[4 * unit])
+                               : __ldg(reinterpret_cast<const float4*>(p.wx + 4 * unit));
+                    if (kb == grp && !x_tma) {     // this group's first k-block of the tile: modulated inputs of its rows
 #pragma unroll
                         for (int i = 0; i < kCells; ++i) {
                             const int64_t r = (int64_t)tile * kTileM + rsub + kRowStep * i;
@@ -407,8 +420,25 @@ __global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_ker
                 }
                 if (TMA) {
                     // this group's raw slot was filled by the producer warp while the group worked on its previous item
-                    const uint8_t* rs = raw + (size_t)grp * kRawSlot;
+                    const uint8_t* rs = raw + (size_t)grp * Cfg::kSlotBytes;
                     mbar_wait(&tail->raw_full[grp], (uint32_t)((j / kGroups) & 1), 1);
+                    if (x_tma && (kb == grp || kb == kBwdNkb - kGroups + grp)) {
+                        // first item of the tile: modulated inputs x*s; last item: raw x for the gate adjoint
+                        const float* rx = reinterpret_cast<const float*>(rs + kRawSlot);
+                        const uint32_t b0 = (uint32_t)(((int64_t)tile * kTileM) % p.b_inner);
+#pragma unroll
+                        for (int i = 0; i < kCells; ++i) {
+                            const int row = rsub + kRowStep * i;
+                            const bool ok = (int64_t)tile * kTileM + row < p.rows;
+                            const float xv = ok ? rx[row * p.t_len + p.t] : 0.f;
+                            if (kb == grp) {
+                                xs[i] = xv * tail->s_sg[(b0 + (uint32_t)row) % (uint32_t)p.b_inner];
+                                dxs[i] = 0.f;
+                            } else {
+                                xraw[i] = xv;
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < kCells; ++i) {
                         const int row = rsub + kRowStep * i;
@@ -542,7 +572,7 @@ __global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_ker
                     d += __shfl_xor_sync(0xffffffffu, d, 2);
                     d += __shfl_xor_sync(0xffffffffu, d, 4);
                     if (c == 0 && r < p.rows) {
-                        const float contrib = d * p.xo[(r * p.t_len + p.t) * p.c_in];
+                        const float contrib = d * (x_tma ? xraw[i] : p.xo[(r * p.t_len + p.t) * p.c_in]);
                         const int64_t b = r % p.b_inner;
                         if (ds_smem) atomicAdd(&tail->s_ds[b], contrib);
                         else atomicAdd(&p.d_s[b * p.t_len + p.t], contrib);
@@ -563,9 +593,13 @@ __global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_ker
                 const int slot = j & 1, n = j >> 1;
                 const int tile = blockIdx.x + (j / kBwdNkb) * gridDim.x, kb = j % kBwdNkb;
                 if (n > 0) mbar_wait_raw(&tail->raw_empty[slot], (uint32_t)((n - 1) & 1));
-                uint8_t* rs = raw + (size_t)slot * kRawSlot;
+                uint8_t* rs = raw + (size_t)slot * Cfg::kSlotBytes;
                 uint64_t* fb = &tail->raw_full[slot];
-                mbar_arrive_expect_tx(fb, bytes);
+                const bool want_x = x_tma && (kb < 2 || kb >= kBwdNkb - 2);
+                const int64_t r0 = (int64_t)tile * kTileM;
+                const uint32_t xbytes = (uint32_t)(((p.rows - r0) < kTileM ? (p.rows - r0) : kTileM) * p.t_len * 4);
+                mbar_arrive_expect_tx(fb, bytes + (want_x ? xbytes : 0u));
+                if (want_x) bulk_g2s(rs + kRawSlot, p.xo + r0 * p.t_len, xbytes, fb);
                 tma_load_2d(rs, &p.gates_map, kb * kKB, tile * kTileM, fb);
                 const int64_t off = ((int64_t)tile * 8 + kb) * (kRawVec / 4);      // tile-blocked (128 x 8) slice
                 uint8_t* v = rs + kRawGates;
