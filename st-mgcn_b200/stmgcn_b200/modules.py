@@ -7,6 +7,7 @@ runs the sm_100a kernels of ``libstmgcn_b200.so`` (no torch einsum / nn.LSTM exe
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -14,6 +15,11 @@ from torch import nn
 
 from . import _lib, ops
 from .graph import ChebSupports, supports_from_dense
+
+
+def _graph_streams_enabled() -> bool:
+    """One CUDA stream per graph branch in ``ST_MGCN.forward`` (``STMGCN_GRAPH_STREAMS=0`` runs them on one stream)."""
+    return os.environ.get("STMGCN_GRAPH_STREAMS", "1") != "0"
 
 
 def _act_code(activation_module) -> Optional[int]:
@@ -168,10 +174,36 @@ class ST_MGCN(nn.Module):
         """``obs_seq``: (B,T,N,C); ``sta_adj_list``: M support stacks -> (B,N,C).  ``STMGCN.py:100-119``."""
         assert len(sta_adj_list) == self.M
         xo, xt = ops.obs_to_node_major(obs_seq)          # shared by all graphs
-        feats = []
+        ssets = []
         for m in range(self.M):
             assert self.sta_K == sta_adj_list[m].shape[0]
-            sset = supports_from_dense(sta_adj_list[m])
-            h_top, _, _ = self.rnn_list[m].forward_node_major(sset, xo, xt)
-            feats.append(self.gcn_list[m].forward_node_major(sset, h_top))
+            ssets.append(supports_from_dense(sta_adj_list[m]))
+        feats = []
+        if self.M > 1 and _graph_streams_enabled() and not torch.cuda.is_current_stream_capturing():
+            # the M graph branches are independent until the fusion: one CUDA stream per branch keeps the device's work
+            # queue full across kernel boundaries (autograd replays each branch's backward on the same stream)
+            main = torch.cuda.current_stream()
+            start = main.record_event()
+            streams = self._branch_streams(obs_seq.device)
+            for m in range(self.M):
+                with torch.cuda.stream(streams[m]):
+                    streams[m].wait_event(start)
+                    h_top, _, _ = self.rnn_list[m].forward_node_major(ssets[m], xo, xt)
+                    feats.append(self.gcn_list[m].forward_node_major(ssets[m], h_top))
+                xo.record_stream(streams[m])
+                xt.record_stream(streams[m])
+            for m in range(self.M):
+                main.wait_stream(streams[m])
+                feats[m].record_stream(main)
+        else:
+            for m in range(self.M):
+                h_top, _, _ = self.rnn_list[m].forward_node_major(ssets[m], xo, xt)
+                feats.append(self.gcn_list[m].forward_node_major(ssets[m], h_top))
         return ops.FuseOut.apply(self.fc.weight, self.fc.bias, *feats)
+
+    def _branch_streams(self, device):
+        cache = getattr(self, "_streams", None)
+        if cache is None or cache[0] != device:
+            cache = (device, [torch.cuda.Stream(device=device) for _ in range(self.M)])
+            object.__setattr__(self, "_streams", cache)
+        return cache[1]
