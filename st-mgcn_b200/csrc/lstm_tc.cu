@@ -182,16 +182,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
         const int q = warp & 3, part = warp >> 2;
         float* stg = reinterpret_cast<float*>(staging + (size_t)warp * kStagingBytes);
         uint32_t tcount = 0;
+        // c_{t-1} of this warp's 16 units is fetched one 4-unit piece ahead of its use, across tile boundaries too
+        // (8 instead of 16 registers live, and the first piece of a tile never waits for its load)
+        float4 cp_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+            const int64_t rf = (int64_t)blockIdx.x * kTileM + q * 32 + lane;
+            if (p.c_prev != nullptr && (int)blockIdx.x < p.n_tiles && rf < p.rows)
+                cp_nxt = *reinterpret_cast<const float4*>(p.c_prev + ws_off(p.blocked_cs, rf, part * 16));
+        }
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
             const int a = tcount & 1;
             const uint32_t aph = (tcount >> 1) & 1;
             const int64_t r0 = (int64_t)tile * kTileM + q * 32;     // first row of this warp
             const int64_t r = r0 + lane;
             const bool valid = r < p.rows;
-            // c_{t-1} of this warp's 16 units, fetched one 4-unit piece ahead of its use (keeps 8 instead of 16 registers live)
-            const float* cprow = (p.c_prev != nullptr && valid) ? p.c_prev + ws_off(p.blocked_cs, r, part * 16) : nullptr;
-            float4 cp_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cprow) cp_nxt = *reinterpret_cast<const float4*>(cprow);
+            const bool cprow = (p.c_prev != nullptr && valid);
             mbar_wait(&bar->tmem_full[a], aph, 3);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * kFwdN + (uint32_t)part * 64;
@@ -201,7 +206,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                 tmem_ld16(t_row + pc * 16, v);
                 const int unit0 = part * 16 + pc * 4;
                 const float cp[4] = {cp_nxt.x, cp_nxt.y, cp_nxt.z, cp_nxt.w};
-                if (pc < 3 && cprow) cp_nxt = *reinterpret_cast<const float4*>(p.c_prev + ws_off(p.blocked_cs, r, unit0 + 4));
+                if (pc < 3) {
+                    if (cprow) cp_nxt = *reinterpret_cast<const float4*>(p.c_prev + ws_off(p.blocked_cs, r, unit0 + 4));
+                } else {                                            // first piece of this CTA's next tile
+                    const int64_t rn = r + (int64_t)gridDim.x * kTileM;
+                    cp_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.c_prev != nullptr && tile + (int)gridDim.x < p.n_tiles && rn < p.rows)
+                        cp_nxt = *reinterpret_cast<const float4*>(p.c_prev + ws_off(p.blocked_cs, rn, part * 16));
+                }
                 tmem_ld_wait();
                 float hn[4], cn[4];
 #pragma unroll
