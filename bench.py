@@ -387,6 +387,59 @@ def run_ours(args, w):
                              f"nnz*F*4 B per launch (see DESIGN.md section 3), not by HBM"}
         del stacks
 
+    # ---- the kernels that dominate the step by time: the shared LSTM of one graph branch, timed alone --------------
+    roofline_lstm = None
+    if rank == 0 and w.lstm_hidden == 64 and w.input_dim == 1:
+        rnn = model.rnn_list[0]
+        lyr, hid, t_len = w.lstm_layers, w.lstm_hidden, w.seq_len
+        rows = w.n_regions * b
+        xo = torch.randn(w.n_regions, b, t_len, 1, device=dev)
+        s_gate = torch.rand(b, t_len, device=dev)
+        wts = [p_.detach().clone().requires_grad_(True) for p_ in rnn._lstm_weights()]
+        d_top = torch.randn(w.n_regions, b, hid, device=dev)
+
+        def lstm_once():
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            torch.cuda.synchronize()
+            l_a = _lib.launch_count()
+            ev[0].record()
+            h_top, _, _ = ops.SharedLSTM.apply(xo, s_gate, None, None, lyr, hid, False, *wts)
+            ev[1].record()
+            l_b = _lib.launch_count()
+            h_top.backward(d_top)
+            ev[2].record()
+            torch.cuda.synchronize()
+            return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), l_b - l_a, _lib.launch_count() - l_b
+
+        for _ in range(2):
+            lstm_once()
+        runs = [lstm_once() for _ in range(3)]
+        ms_f = sum(r[0] for r in runs) / len(runs)
+        ms_b = sum(r[1] for r in runs) / len(runs)
+        u = rows * hid * 4                                    # one (rows, H) fp32 array
+        fwd_u = bwd_u = wg_u = 0
+        for l in range(lyr):
+            for t in range(t_len):
+                fwd_u += (1 if l > 0 else 0) + (2 if t > 0 else 0) + 2 + 4          # h_below, h/c_{t-1} | h, c, gate tape
+                dh_in = 1 if l < lyr - 1 else (1 if t == t_len - 1 else 0)
+                bwd_u += 4 + 1 + (1 if t > 0 else 0) + (2 if t < t_len - 1 else 0) + dh_in     # tape, c_t, c_prev, dh_rec/dc
+                bwd_u += 4 + 2 + (1 if l > 0 else 0)                                           # dA, dc, dh_rec, dx_below
+                wg_u += 4 + (1 if l > 0 else 0) + (1 if t > 0 else 0)                          # dA, h_below, h_{t-1}
+        fwd_b = fwd_u * u + rows * t_len * 4
+        bwd_b = (bwd_u + wg_u) * u + rows * t_len * 4
+        roofline_lstm = {
+            "scope": f"shared {lyr}-layer LSTM of ONE graph branch (rows = N*B = {rows}, H = {hid}, T = {t_len}), timed alone with "
+                     "CUDA events, mean of 3 after 2 warm-ups; algorithmic bytes count every (rows, H) fp32 array a layer-step "
+                     "must read or write once (h_below, h/c_{t-1}, h, c, 4H gate tape; backward: tape, c_t, c_{t-1}, dh, dc, "
+                     "dA, dx; weight gradients: dA + inputs); weights and biases are negligible",
+            "bound": "hbm", "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "forward": {"kernel": "lstm_cell_tc_kernel", "launches": runs[0][2], "ms": ms_f, "algorithmic_bytes": fwd_b,
+                        "achieved": fwd_b / (ms_f * 1e-3) / 1e9, "frac": fwd_b / (ms_f * 1e-3) / 1e9 / pk["hbm_gbs"]},
+            "backward": {"kernel": "lstm_bwd_tc_kernel + lstm_wgrad_tc_kernel", "launches": runs[0][3], "ms": ms_b,
+                         "algorithmic_bytes": bwd_b, "achieved": bwd_b / (ms_b * 1e-3) / 1e9,
+                         "frac": bwd_b / (ms_b * 1e-3) / 1e9 / pk["hbm_gbs"]}}
+        del xo, s_gate, wts, d_top
+
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -398,7 +451,7 @@ def run_ours(args, w):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(w, world, b), cuda_graph=use_graph), "clocks": clocks,
                 "gpu_launches": int(launches),
-                "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "e2e": e2e, "roofline": roofline, "roofline_lstm": roofline_lstm, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

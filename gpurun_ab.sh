@@ -1,8 +1,3 @@
-L=st-mgcn_b200/lib
-run() { python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', d['ms_per_step'], d['value'])"; }
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-run new
-cp $L/base.so $L/libstmgcn_b200.so; run base
-cp $L/new.so $L/libstmgcn_b200.so; run new
-cp $L/base.so $L/libstmgcn_b200.so; run base
-cp $L/new.so $L/libstmgcn_b200.so
+mkdir -p gpurun_out
+python bench.py > gpurun_out/bench_r8_n1.json 2> gpurun_out/bench_r8_n1.err; tail -c 3000 gpurun_out/bench_r8_n1.json
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r8_ref.json 2> gpurun_out/bench_r8_ref.err; tail -c 1200 gpurun_out/bench_r8_ref.json
