@@ -575,7 +575,9 @@ __global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_ker
                     if (p.dh_in) prefetch_l2(p.dh_in + r0 * kHid, bh);
                 }
             }
-            if (l0 && kb == kBwdNkb - kGroups + grp) {     // this group's last k-block of the tile: gate adjoint partial     // gate adjoint: d s[b,t] += dxmod[r] * xo[r,t]   (STMGCN.py:44, C = 1)
+            if (l0 && kb == kBwdNkb - kGroups + grp) {     // this group's last k-block of the tile: gate adjoint partial
+                // d s[b,t] += dxmod[r] * xo[r,t]   (STMGCN.py:44, C = 1); b = r mod B with one 64-bit modulo per tile
+                const uint32_t bt0 = (uint32_t)(row_base % p.b_inner);
 #pragma unroll
                 for (int i = 0; i < kCells; ++i) {
                     const int64_t r = row_base + rsub + kRowStep * i;
@@ -585,7 +587,9 @@ __global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_ker
                     d += __shfl_xor_sync(0xffffffffu, d, 4);
                     if (c == 0 && r < p.rows) {
                         const float contrib = d * (x_tma ? xraw[i] : p.xo[(r * p.t_len + p.t) * p.c_in]);
-                        const int64_t b = r % p.b_inner;
+                        const int64_t b = p.b_inner <= 0x7fffffff
+                                              ? (int64_t)((bt0 + (uint32_t)(rsub + kRowStep * i)) % (uint32_t)p.b_inner)
+                                              : r % p.b_inner;
                         if (ds_smem) atomicAdd(&tail->s_ds[b], contrib);
                         else atomicAdd(&p.d_s[b * p.t_len + p.t], contrib);
                     }

@@ -194,7 +194,7 @@ def test_errors_are_loud():
         ops.obs_to_node_major(torch.randn(2, 3, 4, 1))                               # CPU tensor
 
 
-@pytest.mark.parametrize("rows_n,b,t,c", [(5, 60, 3, 1), (3, 50, 2, 2), (40, 64, 4, 1)])
+@pytest.mark.parametrize("rows_n,b,t,c", [(5, 60, 3, 1), (3, 50, 2, 2), (40, 64, 4, 1), (7, 36, 8, 1), (2, 1100, 4, 1)])
 def test_lstm_tensor_core_path_matches_exact_fp32_path(rows_n, b, t, c):
     """tcgen05 3xTF32 LSTM forward vs the exact-FFMA kernels on the same inputs (ragged 128-row tiles)."""
     from stmgcn_b200 import ops
@@ -223,7 +223,9 @@ def test_lstm_tensor_core_path_matches_exact_fp32_path(rows_n, b, t, c):
         assert_close(a.cpu().numpy(), b_.cpu().numpy(), f"tc vs fma {name}", 2e-5)
 
 
-@pytest.mark.parametrize("rows_n,b,t,c", [(5, 60, 3, 1), (40, 64, 4, 1), (3, 50, 2, 2)])
+# (7, 36, 8): ragged last tile with the TMA-fed layer-0 inputs; (2, 1100, 4): batch larger than the shared-memory gate
+# column (global-atomic adjoint path)
+@pytest.mark.parametrize("rows_n,b,t,c", [(5, 60, 3, 1), (40, 64, 4, 1), (3, 50, 2, 2), (7, 36, 8, 1), (2, 1100, 4, 1)])
 def test_lstm_tensor_core_backward_matches_exact_fp32_path(rows_n, b, t, c):
     """tcgen05 fused BPTT kernel (pointwise in the loader + dA.Wp^T) vs the exact-FFMA kernels: d_s and all
     LSTM weight gradients (C=2 exercises the mixed case: layer 0 on FFMA, layers > 0 on tensor cores)."""
