@@ -45,15 +45,18 @@ constexpr int kFwdStageBytes = 2 * kABytes + 2 * kFwdBBytes;      // 96 KB
 constexpr int kFwdEpiWarps = 16;                                  // 4 per TMEM lane quadrant: the epilogue is
 constexpr int kFwdLoaderWarps = 8;                                // latency-bound, thread-level parallelism pays
 constexpr int kFwdLoaders = kFwdLoaderWarps * 32;
-constexpr int kFwdThreads = (kFwdEpiWarps + kFwdLoaderWarps + 1) * 32;   // 800
+constexpr int kFwdThreads = (kFwdEpiWarps + kFwdLoaderWarps + 2) * 32;   // 832: + MMA warp + TMA producer warp
 constexpr int kStagingBytes = 32 * 16 * 4;                        // per epilogue warp: [32 rows][16 cols] fp32
 
 struct FwdTail {
     float bias[kGateCols];
     Barriers bar;
+    uint64_t a_full[kFwdStages];      // TMA-fed variant: the raw A tile of the stage has landed
 };
 constexpr size_t kFwdSmem = 1024 + (size_t)kFwdStages * kFwdStageBytes + (size_t)kFwdEpiWarps * kStagingBytes +
                             sizeof(FwdTail);
+
+static_assert(kFwdSmem <= 232448, "forward kernel exceeds the 227 KB shared-memory limit");
 
 struct CellParams {
     const float* seg0;       // (rows, 64) first K segment  (h_below for l>0, h_prev for l==0) or nullptr = zeros
@@ -75,9 +78,20 @@ struct CellParams {
     int blocked_cs;          // c_prev / c_out use the tile-blocked layout (see ws_off)
     int prefetch;            // bulk L2 prefetch of the next tile's inputs (STMGCN_TC_PREFETCH=1; default off)
     int gates_tma;           // gate tape leaves through TMA tensor stores (gates_map) instead of per-thread stores
+    int dbg_skip_hc;         // timing experiments only (STMGCN_DBG_SKIP_HC=1): drop the h / c stores (wrong results)
     alignas(64) CUtensorMap gates_map;   // (rows, 256) fp32 slice of the tape, box 32 rows x 16 columns, 64-byte swizzle
+    int hc_tma;                          // h / c leave through TMA tensor stores too (h_map, c_map; needs gates_tma)
+    alignas(64) CUtensorMap h_map;       // (rows, 64) slice of hs, box 32 rows x 4 units
+    alignas(64) CUtensorMap c_map;       // cs slice: (rows, 64) row-major, or (rows_pad * 8, 8) when tile-blocked
+    alignas(64) CUtensorMap seg0_map;    // A_TMA: (rows, 64) slices of the hidden-state tape, box 128 rows x 32 columns,
+    alignas(64) CUtensorMap seg1_map;    //        128-byte swizzle == the K-major operand tile layout
 };
 
+// A_TMA: the raw fp32 A tile of every k-block is written by ONE TMA tensor load straight into the stage's hi tile (the
+// 128-byte TMA swizzle is the operand layout); the loader warps then read it back from shared memory, and write the
+// tf32 hi part in place and the lo part next to it -- no per-thread global loads (whose latency the proxy fence's MEMBAR
+// would expose), the load is issued the moment the MMA warp frees the stage.
+template <bool GATES_TMA, bool A_TMA>
 __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __grid_constant__ CellParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -90,7 +104,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
     constexpr int kMmaWarp = kFwdEpiWarps + kFwdLoaderWarps;
 
     pdl_launch_dependents();
-    if (tid == 0) init_barriers(bar, kFwdStages, kFwdEpiWarps * 32, kFwdLoaders / 2);   // one loader group per k-block
+    if (tid == 0) {
+        for (int s = 0; s < kFwdStages; ++s) mbar_init(&tail->a_full[s], 1);
+        init_barriers(bar, kFwdStages, kFwdEpiWarps * 32, kFwdLoaders / 2);   // one loader group per k-block
+    }
     if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, 512);
     for (int i = tid; i < kGateCols; i += kFwdThreads) tail->bias[i] = p.bias ? p.bias[i] : 0.f;
     pdl_wait();
@@ -116,7 +133,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
         for (int j = grp; j < total; j += kGroups) {
             const int tile = blockIdx.x + (j / p.nkb) * gridDim.x, kb = j % p.nkb;
             float4 buf[kPer];
-            if (p.aux && kb == 2) {                        // auxiliary block: modulated input columns and the constant 1
+            const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
+            const bool aux_blk = p.aux && kb == 2;
+            const bool from_tma = A_TMA && !aux_blk && seg != nullptr;
+            if (aux_blk) {                                 // auxiliary block: modulated input columns and the constant 1
 #pragma unroll
                 for (int i = 0; i < kPer; ++i) {
                     const int64_t r = (int64_t)tile * kTileM + rsub + (kGT / 8) * i;
@@ -132,8 +152,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                     }
                     buf[i] = make_float4(v[0], v[1], v[2], v[3]);
                 }
-            } else {
-                const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
+            } else if (!from_tma) {
                 const int koff = (kb & 1) * kKB + c * 4;
 #pragma unroll
                 for (int i = 0; i < kPer; ++i) {
@@ -144,13 +163,24 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
             }
             const int s = j % kFwdStages;
             const uint32_t ph = (j / kFwdStages) & 1;
-            mbar_wait(&bar->empty[s], ph ^ 1, 0);
             uint8_t* st = smem + (size_t)s * kFwdStageBytes;
-            if (gtid == 0) {
-                mbar_arrive_expect_tx(&bar->full[s], 2 * kFwdBBytes);
-                const float* src = p.wimg + (size_t)kb * (2 * kFwdBBytes / 4);
-                bulk_g2s(st + 2 * kABytes, src, kFwdBBytes, &bar->full[s]);
-                bulk_g2s(st + 2 * kABytes + kFwdBBytes, src + kFwdBBytes / 4, kFwdBBytes, &bar->full[s]);
+            if (A_TMA) {
+                mbar_wait(&tail->a_full[s], ph, 0);        // stage is free and (for TMA blocks) the raw tile is in place
+                if (from_tma) {
+#pragma unroll
+                    for (int i = 0; i < kPer; ++i) {
+                        const int row = rsub + (kGT / 8) * i;
+                        buf[i] = *reinterpret_cast<const float4*>(st + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4));
+                    }
+                }
+            } else {
+                mbar_wait(&bar->empty[s], ph ^ 1, 0);
+                if (gtid == 0) {
+                    mbar_arrive_expect_tx(&bar->full[s], 2 * kFwdBBytes);
+                    const float* src = p.wimg + (size_t)kb * (2 * kFwdBBytes / 4);
+                    bulk_g2s(st + 2 * kABytes, src, kFwdBBytes, &bar->full[s]);
+                    bulk_g2s(st + 2 * kABytes + kFwdBBytes, src + kFwdBBytes / 4, kFwdBBytes, &bar->full[s]);
+                }
             }
 #pragma unroll
             for (int i = 0; i < kPer; ++i) {
@@ -174,6 +204,30 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
         TC_PROF_FLUSH(0, ltid == 0)
     } else if (warp == kMmaWarp) {
         mma_issuer<kFwdN, kFwdStages, 0>(bar, smem, kFwdStageBytes, kFwdBBytes, p.nkb, p.n_tiles, tmem_base, lane);
+    } else if (warp == kMmaWarp + 1) {
+        // ===================== producer (A_TMA): raw A tile + weight images for every freed stage =====================
+        if (A_TMA && lane == 0) {
+            const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int total = my_tiles * p.nkb;
+            for (int j = 0; j < total; ++j) {
+                const int tile = blockIdx.x + (j / p.nkb) * gridDim.x, kb = j % p.nkb;
+                const int s = j % kFwdStages;
+                const uint32_t ph = (j / kFwdStages) & 1;
+                mbar_wait_raw(&bar->empty[s], ph ^ 1);
+                uint8_t* st = smem + (size_t)s * kFwdStageBytes;
+                const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
+                if (!(p.aux && kb == 2) && seg != nullptr) {
+                    mbar_arrive_expect_tx(&tail->a_full[s], kABytes);
+                    tma_load_2d(st, (kb >> 1) ? &p.seg1_map : &p.seg0_map, (kb & 1) * kKB, tile * kTileM, &tail->a_full[s]);
+                } else {
+                    mbar_arrive(&tail->a_full[s]);         // the loaders build this block themselves
+                }
+                mbar_arrive_expect_tx(&bar->full[s], 2 * kFwdBBytes);
+                const float* src = p.wimg + (size_t)kb * (2 * kFwdBBytes / 4);
+                bulk_g2s(st + 2 * kABytes, src, kFwdBBytes, &bar->full[s]);
+                bulk_g2s(st + 2 * kABytes + kFwdBBytes, src + kFwdBBytes / 4, kFwdBBytes, &bar->full[s]);
+            }
+        }
     } else {
         // ===================== epilogue: LSTM cell =====================
         // 16 warps: TMEM lane quadrant q = warp & 3 (rows 32q..32q+31 of the tile), column quarter part = warp >> 2
@@ -182,21 +236,26 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
         const int q = warp & 3, part = warp >> 2;
         float* stg = reinterpret_cast<float*>(staging + (size_t)warp * kStagingBytes);
         uint32_t tcount = 0;
-        // c_{t-1} of this warp's 16 units is fetched one 4-unit piece ahead of its use, across tile boundaries too
-        // (8 instead of 16 registers live, and the first piece of a tile never waits for its load)
-        float4 cp_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-        {
-            const int64_t rf = (int64_t)blockIdx.x * kTileM + q * 32 + lane;
-            if (p.c_prev != nullptr && (int)blockIdx.x < p.n_tiles && rf < p.rows)
-                cp_nxt = *reinterpret_cast<const float4*>(p.c_prev + ws_off(p.blocked_cs, rf, part * 16));
-        }
+        // c_{t-1} of this warp's 16 units for a whole tile is fetched one TILE ahead, right after the last proxy fence of
+        // the previous tile: the MEMBAR inside fence.proxy.async waits for every outstanding load of the thread, so a
+        // load issued inside the piece loop would cost each piece a full DRAM latency
+        float4 cpv[4];
+        auto fetch_cprev = [&](int tile_n) {
+            const int64_t rn = (int64_t)tile_n * kTileM + q * 32 + lane;
+            const bool okn = p.c_prev != nullptr && tile_n < p.n_tiles && rn < p.rows;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cpv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (okn) cpv[j] = *reinterpret_cast<const float4*>(p.c_prev + ws_off(p.blocked_cs, rn, part * 16 + 4 * j));
+            }
+        };
+        fetch_cprev((int)blockIdx.x);
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
             const int a = tcount & 1;
             const uint32_t aph = (tcount >> 1) & 1;
             const int64_t r0 = (int64_t)tile * kTileM + q * 32;     // first row of this warp
             const int64_t r = r0 + lane;
             const bool valid = r < p.rows;
-            const bool cprow = (p.c_prev != nullptr && valid);
             mbar_wait(&bar->tmem_full[a], aph, 3);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * kFwdN + (uint32_t)part * 64;
@@ -205,15 +264,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                 uint32_t v[16];
                 tmem_ld16(t_row + pc * 16, v);
                 const int unit0 = part * 16 + pc * 4;
-                const float cp[4] = {cp_nxt.x, cp_nxt.y, cp_nxt.z, cp_nxt.w};
-                if (pc < 3) {
-                    if (cprow) cp_nxt = *reinterpret_cast<const float4*>(p.c_prev + ws_off(p.blocked_cs, r, unit0 + 4));
-                } else {                                            // first piece of this CTA's next tile
-                    const int64_t rn = r + (int64_t)gridDim.x * kTileM;
-                    cp_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.c_prev != nullptr && tile + (int)gridDim.x < p.n_tiles && rn < p.rows)
-                        cp_nxt = *reinterpret_cast<const float4*>(p.c_prev + ws_off(p.blocked_cs, rn, part * 16));
-                }
+                const float cp[4] = {cpv[pc].x, cpv[pc].y, cpv[pc].z, cpv[pc].w};
                 tmem_ld_wait();
                 float hn[4], cn[4];
 #pragma unroll
@@ -235,7 +286,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                 if (p.gates_out != nullptr) {
                     // gate tape: this warp's [32 rows][16 columns] piece goes through its staging tile (16-byte chunks
                     // XOR-swizzled with (row >> 1) & 3 == the TMA 64-byte swizzle, conflict-free for the lanes)
-                    if (p.gates_tma) {                 // previous piece's tensor store must have read the tile
+                    if (GATES_TMA) {                   // previous piece's tensor store must have read the tile
                         if (lane == 0) bulk_wait_read0();
                     }
                     __syncwarp();
@@ -243,7 +294,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                     for (int u = 0; u < 4; ++u)
                         *reinterpret_cast<uint4*>(stg + lane * 16 + ((u ^ ((lane >> 1) & 3)) << 2)) =
                             make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-                    if (p.gates_tma) {
+                    if (GATES_TMA) {
                         // one TMA tensor store per piece: no per-thread global stores, rows past the end are clipped
                         fence_proxy_async_smem();
                         __syncwarp();
@@ -263,16 +314,35 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
                         }
                     }
                 }
-                // h / c after the tape hand-off: the proxy fence above does not have to wait for these stores
-                if (valid) {
+                if (GATES_TMA && p.hc_tma) {
+                    // h / c through the same staging tile once the tape store has read it: the epilogue threads then
+                    // issue no global stores at all, so the proxy fences (MEMBAR) have nothing outstanding to wait for
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
+                    *reinterpret_cast<float4*>(stg + lane * 4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                    *reinterpret_cast<float4*>(stg + 128 + lane * 4) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&p.h_map, smem_u32(stg), unit0, (int)r0);
+                        if (p.blocked_cs)
+                            tma_store_2d(&p.c_map, smem_u32(stg + 128), unit0 & 7,
+                                         (tile * 8 + (unit0 >> 3)) * kTileM + q * 32);
+                        else
+                            tma_store_2d(&p.c_map, smem_u32(stg + 128), unit0, (int)r0);
+                        bulk_commit_group();
+                    }
+                } else if (valid && !p.dbg_skip_hc) {
+                    // h / c after the tape hand-off: the proxy fence above does not have to wait for these stores
                     *reinterpret_cast<float4*>(p.h_out + r * kHid + unit0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                     *reinterpret_cast<float4*>(p.c_out + ws_off(p.blocked_cs, r, unit0)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                 }
             }
+            fetch_cprev(tile + (int)gridDim.x);
             tc_fence_before();
             mbar_arrive(&bar->tmem_empty[a]);
         }
-        if (p.gates_tma && lane == 0) bulk_wait0();      // shared memory stays valid until the last tensor store is done
+        if (GATES_TMA && lane == 0) bulk_wait0();      // shared memory stays valid until the last tensor store is done
         TC_PROF_FLUSH(2, tid == 0)
     }
     tc_fence_before();
@@ -931,20 +1001,31 @@ static EncodeTiledFn encode_tiled_fn() {
     }
     return fn;
 }
-// (rows, 256) fp32 row-major slice of the gate tape, box = box_rows x box_cols
-static bool make_gates_map(CUtensorMap* map, float* base, int64_t rows, int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+// (rows, cols) fp32 row-major matrix, box = box_rows x box_cols
+static bool make_tile_map(CUtensorMap* map, const float* base, int64_t rows, int cols, int box_cols, int box_rows,
+                          CUtensorMapSwizzle swz) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (fn == nullptr) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)kGateCols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)kGateCols * sizeof(float)};
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+static bool make_gates_map(CUtensorMap* map, float* base, int64_t rows, int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+    return make_tile_map(map, base, rows, kGateCols, box_cols, box_rows, swz);
+}
+
 static int env_flag(const char* name, int dflt) {
     const char* e = getenv(name);
     return e == nullptr ? dflt : (e[0] != '0');
+}
+static int fwd_tma_enabled() {        // forward: A operand tiles through TMA tensor loads (STMGCN_FWD_TMA=0 disables)
+    static int v = -1;
+    if (v < 0) v = env_flag("STMGCN_FWD_TMA", 1);
+    return v;
 }
 static int gates_tma_enabled() {      // forward: gate tape through TMA tensor stores (STMGCN_GATES_TMA=0 disables)
     static int v = -1;
@@ -965,7 +1046,10 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
                             int blocked_cs, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        STMGCN_CUDA(cudaFuncSetAttribute(lstm_cell_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_cell_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_cell_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_cell_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_cell_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
         attr_done = true;
     }
     CellParams p;
@@ -990,11 +1074,41 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
     p.blocked_cs = blocked_cs;
     p.prefetch = tc_prefetch_enabled();
     p.gates_tma = 0;
+    {
+        static int skip = -1;
+        if (skip < 0) skip = env_flag("STMGCN_DBG_SKIP_HC", 0);
+        p.dbg_skip_hc = skip;
+    }
     memset(&p.gates_map, 0, sizeof(p.gates_map));
     if (gates_out != nullptr && gates_tma_enabled() && make_gates_map(&p.gates_map, gates_out, rows, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B))
         p.gates_tma = 1;
     const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-    STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel, grid, kFwdThreads, kFwdSmem, st, p));
+    // h / c through TMA stores (STMGCN_HC_TMA=0 disables): box = 32 rows x 4 units
+    p.hc_tma = 0;
+    memset(&p.h_map, 0, sizeof(p.h_map));
+    memset(&p.c_map, 0, sizeof(p.c_map));
+    {
+        static int hc = -1;
+        if (hc < 0) hc = env_flag("STMGCN_HC_TMA", 1);
+        if (hc && p.gates_tma && !p.dbg_skip_hc &&
+            make_tile_map(&p.h_map, h_out, rows, kHid, 4, 32, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+            (blocked_cs ? make_tile_map(&p.c_map, c_out, (int64_t)p.n_tiles * 8 * kTileM, 8, 4, 32, CU_TENSOR_MAP_SWIZZLE_NONE)
+                        : make_tile_map(&p.c_map, c_out, rows, kHid, 4, 32, CU_TENSOR_MAP_SWIZZLE_NONE)))
+            p.hc_tma = 1;
+    }
+    // A operand through TMA: one tensor map per (rows, 64) hidden-state slice (absent segments are built as zeros)
+    memset(&p.seg0_map, 0, sizeof(p.seg0_map));
+    memset(&p.seg1_map, 0, sizeof(p.seg1_map));
+    bool a_tma = fwd_tma_enabled() != 0;
+    if (a_tma && seg0) a_tma = make_tile_map(&p.seg0_map, seg0, rows, kHid, kKB, kTileM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (a_tma && seg1) a_tma = make_tile_map(&p.seg1_map, seg1, rows, kHid, kKB, kTileM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (p.gates_tma) {
+        if (a_tma) STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<true, true>, grid, kFwdThreads, kFwdSmem, st, p));
+        else STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<true, false>, grid, kFwdThreads, kFwdSmem, st, p));
+    } else {
+        if (a_tma) STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<false, true>, grid, kFwdThreads, kFwdSmem, st, p));
+        else STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<false, false>, grid, kFwdThreads, kFwdSmem, st, p));
+    }
     count_launch();
     return check_launch("lstm_cell_tc");
 }
