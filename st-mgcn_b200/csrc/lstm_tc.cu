@@ -43,9 +43,15 @@ constexpr int kFwdStages = 2;
 constexpr int kFwdBBytes = kFwdN * kKB * 4;                       // 32 KB
 constexpr int kFwdStageBytes = 2 * kABytes + 2 * kFwdBBytes;      // 96 KB
 constexpr int kFwdEpiWarps = 16;                                  // 4 per TMEM lane quadrant: the epilogue is
-constexpr int kFwdLoaderWarps = 8;                                // latency-bound, thread-level parallelism pays
-constexpr int kFwdLoaders = kFwdLoaderWarps * 32;
-constexpr int kFwdThreads = (kFwdEpiWarps + kFwdLoaderWarps + 2) * 32;   // 832: + MMA warp + TMA producer warp
+// 8 loader warps.  Register loads from HBM: two groups alternate k-blocks (their load latencies overlap).  TMA-fed: one
+// group of all 8 warps per k-block (nothing to overlap, the split latency of a k-block halves); 4 warps were measured
+// slower (6.55 vs 5.42 ms per branch forward).
+template <bool A_TMA> struct FwdCfg {
+    static constexpr int kLoaderWarps = 8;
+    static constexpr int kGroups = A_TMA ? 1 : 2;
+    static constexpr int kLoaders = kLoaderWarps * 32;
+    static constexpr int kThreads = (kFwdEpiWarps + kLoaderWarps + 2) * 32;   // + MMA warp + TMA producer warp
+};
 constexpr int kStagingBytes = 32 * 16 * 4;                        // per epilogue warp: [32 rows][16 cols] fp32
 
 struct FwdTail {
@@ -92,7 +98,10 @@ struct CellParams {
 // tf32 hi part in place and the lo part next to it -- no per-thread global loads (whose latency the proxy fence's MEMBAR
 // would expose), the load is issued the moment the MMA warp frees the stage.
 template <bool GATES_TMA, bool A_TMA>
-__global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __grid_constant__ CellParams p) {
+__global__ void __launch_bounds__((FwdCfg<A_TMA>::kThreads), 1) lstm_cell_tc_kernel(const __grid_constant__ CellParams p) {
+    constexpr int kFwdLoaderWarps = FwdCfg<A_TMA>::kLoaderWarps;
+    constexpr int kFwdLoaders = FwdCfg<A_TMA>::kLoaders;
+    constexpr int kFwdThreads = FwdCfg<A_TMA>::kThreads;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* staging = smem + (size_t)kFwdStages * kFwdStageBytes;
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
     pdl_launch_dependents();
     if (tid == 0) {
         for (int s = 0; s < kFwdStages; ++s) mbar_init(&tail->a_full[s], 1);
-        init_barriers(bar, kFwdStages, kFwdEpiWarps * 32, kFwdLoaders / 2);   // one loader group per k-block
+        init_barriers(bar, kFwdStages, kFwdEpiWarps * 32, kFwdLoaders / FwdCfg<A_TMA>::kGroups);   // one loader group per k-block
     }
     if (warp == kMmaWarp) tmem_alloc(&bar->tmem_base, 512);
     for (int i = tid; i < kGateCols; i += kFwdThreads) tail->bias[i] = p.bias ? p.bias[i] : 0.f;
@@ -124,7 +133,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
         // GROUPS that alternate k-blocks (group g owns k-blocks g, g+2, ... of this CTA's sequence): while one group
         // waits for its loads, the other converts / stores / fences.
         TC_PROF_DECL
-        constexpr int kGroups = 2, kGT = kFwdLoaders / kGroups, kPer = 1024 / kGT;      // float4 per thread per k-block
+        constexpr int kGroups = FwdCfg<A_TMA>::kGroups, kGT = kFwdLoaders / kGroups, kPer = 1024 / kGT;   // float4 per thread per k-block
         const int ltid = tid - kFwdEpiWarps * 32;
         const int grp = ltid / kGT, gtid = ltid % kGT;
         const int c = gtid & 7, rsub = gtid >> 3;          // rows rsub + (kGT/8)*i, 16-byte chunk c of the 128-byte row
@@ -132,60 +141,63 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_cell_tc_kernel(const __gr
         const int total = my_tiles * p.nkb;
         for (int j = grp; j < total; j += kGroups) {
             const int tile = blockIdx.x + (j / p.nkb) * gridDim.x, kb = j % p.nkb;
-            float4 buf[kPer];
+            constexpr int kChunk = kPer < 8 ? kPer : 8;    // float4 per thread in flight
+            static_assert(kPer % kChunk == 0 && (A_TMA || kPer == kChunk), "loader mapping");
             const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
             const bool aux_blk = p.aux && kb == 2;
             const bool from_tma = A_TMA && !aux_blk && seg != nullptr;
-            if (aux_blk) {                                 // auxiliary block: modulated input columns and the constant 1
-#pragma unroll
-                for (int i = 0; i < kPer; ++i) {
-                    const int64_t r = (int64_t)tile * kTileM + rsub + (kGT / 8) * i;
-                    float v[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (c < 2 && r < p.rows) {
-                        const float sv = p.sg[(r % p.b_inner) * p.t_len + p.t];
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const int col = 4 * c + jj;
-                            if (col < p.c_in) v[jj] = p.xo[(r * p.t_len + p.t) * p.c_in + col] * sv;
-                            else if (col == p.c_in) v[jj] = 1.0f;
-                        }
-                    }
-                    buf[i] = make_float4(v[0], v[1], v[2], v[3]);
-                }
-            } else if (!from_tma) {
-                const int koff = (kb & 1) * kKB + c * 4;
-#pragma unroll
-                for (int i = 0; i < kPer; ++i) {
-                    const int64_t r = (int64_t)tile * kTileM + rsub + (kGT / 8) * i;
-                    buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (seg != nullptr && r < p.rows) buf[i] = *reinterpret_cast<const float4*>(seg + r * kHid + koff);
-                }
-            }
             const int s = j % kFwdStages;
             const uint32_t ph = (j / kFwdStages) & 1;
             uint8_t* st = smem + (size_t)s * kFwdStageBytes;
-            if (A_TMA) {
-                mbar_wait(&tail->a_full[s], ph, 0);        // stage is free and (for TMA blocks) the raw tile is in place
-                if (from_tma) {
+            if (A_TMA) mbar_wait(&tail->a_full[s], ph, 0);     // stage is free and (for TMA blocks) the raw tile is in place
+#pragma unroll 1
+            for (int h0 = 0; h0 < kPer; h0 += kChunk) {
+                float4 buf[kChunk];
+                if (aux_blk) {                             // auxiliary block: modulated input columns and the constant 1
 #pragma unroll
-                    for (int i = 0; i < kPer; ++i) {
-                        const int row = rsub + (kGT / 8) * i;
+                    for (int i = 0; i < kChunk; ++i) {
+                        const int64_t r = (int64_t)tile * kTileM + rsub + (kGT / 8) * (h0 + i);
+                        float v[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (c < 2 && r < p.rows) {
+                            const float sv = p.sg[(r % p.b_inner) * p.t_len + p.t];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int col = 4 * c + jj;
+                                if (col < p.c_in) v[jj] = p.xo[(r * p.t_len + p.t) * p.c_in + col] * sv;
+                                else if (col == p.c_in) v[jj] = 1.0f;
+                            }
+                        }
+                        buf[i] = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                } else if (from_tma) {
+#pragma unroll
+                    for (int i = 0; i < kChunk; ++i) {
+                        const int row = rsub + (kGT / 8) * (h0 + i);
                         buf[i] = *reinterpret_cast<const float4*>(st + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4));
                     }
-                }
-            } else {
-                mbar_wait(&bar->empty[s], ph ^ 1, 0);
-                if (gtid == 0) {
-                    mbar_arrive_expect_tx(&bar->full[s], 2 * kFwdBBytes);
-                    const float* src = p.wimg + (size_t)kb * (2 * kFwdBBytes / 4);
-                    bulk_g2s(st + 2 * kABytes, src, kFwdBBytes, &bar->full[s]);
-                    bulk_g2s(st + 2 * kABytes + kFwdBBytes, src + kFwdBBytes / 4, kFwdBBytes, &bar->full[s]);
-                }
-            }
+                } else {
+                    const int koff = (kb & 1) * kKB + c * 4;
 #pragma unroll
-            for (int i = 0; i < kPer; ++i) {
-                const int row = rsub + (kGT / 8) * i;
-                split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), buf[i]);
+                    for (int i = 0; i < kChunk; ++i) {
+                        const int64_t r = (int64_t)tile * kTileM + rsub + (kGT / 8) * (h0 + i);
+                        buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (seg != nullptr && r < p.rows) buf[i] = *reinterpret_cast<const float4*>(seg + r * kHid + koff);
+                    }
+                }
+                if (!A_TMA) {
+                    mbar_wait(&bar->empty[s], ph ^ 1, 0);
+                    if (gtid == 0) {
+                        mbar_arrive_expect_tx(&bar->full[s], 2 * kFwdBBytes);
+                        const float* src = p.wimg + (size_t)kb * (2 * kFwdBBytes / 4);
+                        bulk_g2s(st + 2 * kABytes, src, kFwdBBytes, &bar->full[s]);
+                        bulk_g2s(st + 2 * kABytes + kFwdBBytes, src + kFwdBBytes / 4, kFwdBBytes, &bar->full[s]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < kChunk; ++i) {
+                    const int row = rsub + (kGT / 8) * (h0 + i);
+                    split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), buf[i]);
+                }
             }
             fence_proxy_async_smem();
             mbar_arrive(&bar->full[s]);
@@ -1103,11 +1115,11 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
     if (a_tma && seg0) a_tma = make_tile_map(&p.seg0_map, seg0, rows, kHid, kKB, kTileM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (a_tma && seg1) a_tma = make_tile_map(&p.seg1_map, seg1, rows, kHid, kKB, kTileM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (p.gates_tma) {
-        if (a_tma) STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<true, true>, grid, kFwdThreads, kFwdSmem, st, p));
-        else STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<true, false>, grid, kFwdThreads, kFwdSmem, st, p));
+        if (a_tma) STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<true, true>, grid, FwdCfg<true>::kThreads, kFwdSmem, st, p));
+        else STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<true, false>, grid, FwdCfg<false>::kThreads, kFwdSmem, st, p));
     } else {
-        if (a_tma) STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<false, true>, grid, kFwdThreads, kFwdSmem, st, p));
-        else STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<false, false>, grid, kFwdThreads, kFwdSmem, st, p));
+        if (a_tma) STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<false, true>, grid, FwdCfg<true>::kThreads, kFwdSmem, st, p));
+        else STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<false, false>, grid, FwdCfg<false>::kThreads, kFwdSmem, st, p));
     }
     count_launch();
     return check_launch("lstm_cell_tc");
