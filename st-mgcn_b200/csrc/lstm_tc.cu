@@ -953,6 +953,205 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+
+// ---- TMA-fed variant of the LSTM weight-gradient reduction (N = 256); opt-in, measured slower (see launch_wgrad_tc) -----
+// Same MMA formulation, K = 16 rows per operand stage.  A producer thread streams every 16-row item -- the rows of
+// h_below / h_{t-1} (2 x 4 KB) and of dA (16 KB) are contiguous in HBM, so plain bulk copies do -- into a ring of four
+// 24 KB raw slots, up to four items ahead of the arithmetic; the 16 loader warps (one group) only read shared memory,
+// split to tf32 hi/lo and write the MN-major operand atoms.
+constexpr int kWtRows = 16;
+constexpr int kWtStages = 2;
+constexpr int kWtSlots = 4;
+constexpr int kWtN = kGateCols;
+constexpr int kWtABytes = 128 * kWtRows * 4;                      // 8 KB
+constexpr int kWtBBytes = kWtN * kWtRows * 4;                     // 16 KB
+constexpr int kWtStageBytes = 2 * kWtABytes + 2 * kWtBBytes;      // 48 KB
+constexpr int kWtRawSeg = kWtRows * kHid * 4;                     // 4 KB
+constexpr int kWtRawDa = kWtRows * kWtN * 4;                      // 16 KB
+constexpr int kWtRawBytes = 2 * kWtRawSeg + kWtRawDa;             // 24 KB
+constexpr int kWtThreads = (kWgLoaderWarps + 2) * 32;             // 16 loader warps + MMA warp + producer warp
+struct WtTail {
+    uint64_t full[kWtStages];
+    uint64_t empty[kWtStages];
+    uint64_t raw_full[kWtSlots];
+    uint64_t raw_empty[kWtSlots];
+    uint64_t done;
+    uint32_t tmem_base;
+};
+constexpr size_t kWtSmem = 1024 + (size_t)kWtStages * kWtStageBytes + (size_t)kWtSlots * kWtRawBytes + sizeof(WtTail);
+static_assert(kWtSmem <= 232448, "wgrad TMA kernel exceeds the 227 KB shared-memory limit");
+
+__global__ void __launch_bounds__(kWtThreads, 1) lstm_wgrad_tma_kernel(const __grid_constant__ WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* raw = smem + (size_t)kWtStages * kWtStageBytes;
+    WtTail* tail = (WtTail*)(raw + (size_t)kWtSlots * kWtRawBytes);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    constexpr int kMmaWarp = kWgLoaderWarps;
+    constexpr int kLoaders = kWgLoaderWarps * 32;
+    constexpr int N = kWtN;
+
+    pdl_launch_dependents();
+    if (tid == 0) {
+        for (int s = 0; s < kWtStages; ++s) {
+            mbar_init(&tail->full[s], kLoaders);
+            mbar_init(&tail->empty[s], 1);
+        }
+        for (int s = 0; s < kWtSlots; ++s) {
+            mbar_init(&tail->raw_full[s], 1);
+            mbar_init(&tail->raw_empty[s], kLoaders);
+        }
+        mbar_init(&tail->done, 1);
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, N);
+    pdl_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+    const int64_t chunks_per_t = (p.rows + kWtRows - 1) / kWtRows;
+    const int64_t total_chunks = chunks_per_t * p.t_len;
+    const bool has_work = (int64_t)blockIdx.x < total_chunks;
+    const int64_t my_chunks = has_work ? (total_chunks - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp < kMmaWarp) {
+        // ===================== loaders: raw slot -> tf32 hi/lo -> MN-major swizzled atoms =====================
+        TC_PROF_DECL
+        for (int64_t j = 0; j < my_chunks; ++j) {
+            const int64_t chunk = blockIdx.x + j * gridDim.x;
+            const int t = (int)(chunk / chunks_per_t);
+            const int64_t r0 = (chunk % chunks_per_t) * kWtRows;
+            const int nrow = (int)((p.rows - r0) < kWtRows ? (p.rows - r0) : kWtRows);
+            const bool have0 = (p.kd == 128) && p.seg0 != nullptr;
+            const bool have1 = p.shift1 ? ((t > 0) || p.h0 != nullptr) : true;
+            const int slot = (int)(j % kWtSlots);
+            const uint8_t* rs = raw + (size_t)slot * kWtRawBytes;
+            mbar_wait(&tail->raw_full[slot], (uint32_t)((j / kWtSlots) & 1), 1);
+            float4 va, vb[2];
+            {
+                const int row = tid >> 5, q = tid & 31;        // A': 16 rows x 32 float4 (128 kd values)
+                // kd = 128: m 0..63 from seg0 (h_below), 64..127 from seg1 (h_prev); kd = 64: m 0..63 from seg1
+                const bool from1 = (p.kd == 128) ? (q >= 16) : (q < 16);
+                const bool ok = row < nrow && ((p.kd == 128) ? (from1 ? have1 : have0) : (from1 && have1));
+                va = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) va = *reinterpret_cast<const float4*>(rs + (from1 ? kWtRawSeg : 0) + row * (kHid * 4) + (q & 15) * 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {                      // B': 16 rows x 64 float4
+                const int idx = tid + i * kLoaders;
+                const int row = idx >> 6, q = idx & 63;
+                vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < nrow) vb[i] = *reinterpret_cast<const float4*>(rs + 2 * kWtRawSeg + row * (N * 4) + q * 16);
+            }
+            mbar_arrive(&tail->raw_empty[slot]);
+            const int s = (int)(j % kWtStages);
+            const uint32_t ph = (uint32_t)(j / kWtStages) & 1;
+            mbar_wait(&tail->empty[s], ph ^ 1, 0);
+            uint8_t* st = smem + (size_t)s * kWtStageBytes;
+            {
+                float4 hi, lo;
+                hi.x = tf32_hi(va.x); hi.y = tf32_hi(va.y); hi.z = tf32_hi(va.z); hi.w = tf32_hi(va.w);
+                lo.x = tf32_lo(va.x, hi.x); lo.y = tf32_lo(va.y, hi.y); lo.z = tf32_lo(va.z, hi.z); lo.w = tf32_lo(va.w, hi.w);
+                const uint32_t off = mn32_offset(tid & 31, tid >> 5, kWtRows);
+                *reinterpret_cast<float4*>(st + off) = hi;
+                *reinterpret_cast<float4*>(st + kWtABytes + off) = lo;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = tid + i * kLoaders;
+                const uint32_t off = mn32_offset(idx & 63, idx >> 6, kWtRows);
+                float4 hi, lo;
+                const float4 v = vb[i];
+                hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+                lo.x = tf32_lo(v.x, hi.x); lo.y = tf32_lo(v.y, hi.y); lo.z = tf32_lo(v.z, hi.z); lo.w = tf32_lo(v.w, hi.w);
+                *reinterpret_cast<float4*>(st + 2 * kWtABytes + off) = hi;
+                *reinterpret_cast<float4*>(st + 2 * kWtABytes + kWtBBytes + off) = lo;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&tail->full[s]);
+        }
+        TC_PROF_FLUSH(9, tid == 0)
+        // ===================== epilogue (warps 0-3): accumulator rows = kd index -> red.add into dWp =====================
+        if (warp < 4 && has_work) {
+            mbar_wait(&tail->done, 0, 3);
+            tc_fence_after();
+            const int m = warp * 32 + lane;
+            const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int chunk32 = 0; chunk32 < N / 32; ++chunk32) {
+                uint32_t v[32];
+                tmem_ld32(t_row + chunk32 * 32, v);
+                tmem_ld_wait();
+                if (m < p.kd) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(p.dwp + (int64_t)m * N + chunk32 * 32 + j, __uint_as_float(v[j]));
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = idesc_tf32(128, N, 1);          // both operands MN-major
+        constexpr uint32_t kLbo = (kWtRows / 4) * 512, kSbo = 512;
+        TC_PROF_DECL
+        for (int64_t it = 0; it < my_chunks; ++it) {
+            const int s = (int)(it % kWtStages);
+            const uint32_t ph = (uint32_t)(it / kWtStages) & 1;
+            mbar_wait(&tail->full[s], ph, 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = smem_u32(smem + (size_t)s * kWtStageBytes);
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a_base = st + ((pass == 1) ? kWtABytes : 0);
+                    const uint32_t b_base = st + 2 * kWtABytes + ((pass == 2) ? kWtBBytes : 0);
+#pragma unroll
+                    for (int ks = 0; ks < kWtRows / 8; ++ks) {      // one MMA consumes K = 8 rows = two 4-row atoms
+                        const uint64_t da = smem_desc_mn_sw128(a_base + ks * 2 * kSbo, kLbo, kSbo, 1);
+                        const uint64_t db = smem_desc_mn_sw128(b_base + ks * 2 * kSbo, kLbo, kSbo, 1);
+                        mma_tf32(tmem_base, da, db, idesc, (it > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+                    }
+                }
+                mma_commit(&tail->empty[s]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && has_work) mma_commit(&tail->done);
+        __syncwarp();
+        TC_PROF_FLUSH(10, lane == 0)
+    } else {
+        // ===================== producer: bulk copies of the raw rows, up to kWtSlots items ahead =====================
+        if (lane == 0) {
+            for (int64_t j = 0; j < my_chunks; ++j) {
+                const int64_t chunk = blockIdx.x + j * gridDim.x;
+                const int t = (int)(chunk / chunks_per_t);
+                const int64_t r0 = (chunk % chunks_per_t) * kWtRows;
+                const uint32_t nrow = (uint32_t)((p.rows - r0) < kWtRows ? (p.rows - r0) : kWtRows);
+                const float* s0 = (p.kd == 128 && p.seg0) ? p.seg0 + (int64_t)t * p.rows * kHid : nullptr;
+                const float* s1 = p.shift1 ? ((t > 0) ? p.seg1 + (int64_t)(t - 1) * p.rows * kHid : p.h0)
+                                            : p.seg1 + (int64_t)t * p.rows * kHid;
+                const float* dt = p.da + (int64_t)t * p.rows * N;
+                const int slot = (int)(j % kWtSlots);
+                const int64_t n = j / kWtSlots;
+                if (n > 0) mbar_wait_raw(&tail->raw_empty[slot], (uint32_t)((n - 1) & 1));
+                uint8_t* rs = raw + (size_t)slot * kWtRawBytes;
+                uint64_t* fb = &tail->raw_full[slot];
+                const uint32_t seg_b = nrow * kHid * 4, da_b = nrow * N * 4;
+                mbar_arrive_expect_tx(fb, (s0 ? seg_b : 0u) + (s1 ? seg_b : 0u) + da_b);
+                if (s0) bulk_g2s(rs, s0 + r0 * kHid, seg_b, fb);
+                if (s1) bulk_g2s(rs + kWtRawSeg, s1 + r0 * kHid, seg_b, fb);
+                bulk_g2s(rs + 2 * kWtRawSeg, dt + r0 * N, da_b, fb);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, N);
+}
+
 }  // namespace
 
 namespace stmgcn {
@@ -1193,6 +1392,7 @@ int32_t launch_wgrad_tc(const float* seg0, const float* seg1, const float* h0, i
                                          (int)WgCfg<256>::kSmem));
         STMGCN_CUDA(cudaFuncSetAttribute(lstm_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)WgCfg<64>::kSmem));
+        STMGCN_CUDA(cudaFuncSetAttribute(lstm_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtSmem));
         attr_done = true;
     }
     WgParams p;
@@ -1208,7 +1408,16 @@ int32_t launch_wgrad_tc(const float* seg0, const float* seg1, const float* h0, i
     p.chunks_per_t = ceil_div(rows, kWgRows);
     p.total_chunks = p.chunks_per_t * t_len;
     const int64_t grid = p.total_chunks < sm_count() ? p.total_chunks : sm_count();
-    if (n == 256)
+    // TMA-fed variant for the LSTM shape: opt-in (STMGCN_WGRAD_TMA=1).  Measured on B200 at cfg3, same box: backward of one
+    // branch 10.4 ms with it vs 9.9 ms with the register-load kernel -- its 16-row items double the per-byte cost of
+    // fences and barriers, and the register-load loaders were 81 % busy, not starved.
+    static int wg_tma = -1;
+    if (wg_tma < 0) wg_tma = env_flag("STMGCN_WGRAD_TMA", 0);
+    if (n == 256 && wg_tma && shift1 == 1) {
+        const int64_t total16 = ceil_div(rows, kWtRows) * t_len;
+        const int64_t grid16 = total16 < sm_count() ? total16 : sm_count();
+        STMGCN_CUDA(launch_pdl(lstm_wgrad_tma_kernel, (int)grid16, kWtThreads, kWtSmem, st, p));
+    } else if (n == 256)
         STMGCN_CUDA(launch_pdl(lstm_wgrad_tc_kernel<256>, (int)grid, kWgThreads, WgCfg<256>::kSmem, st, p));
     else
         STMGCN_CUDA(launch_pdl(lstm_wgrad_tc_kernel<64>, (int)grid, kWgThreads, WgCfg<64>::kSmem, st, p));
