@@ -35,8 +35,23 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // ---- device helpers ---------------------------------------------------------------------------------
 // sigmoid / tanh on the MUFU pipe: ex2.approx + rcp.approx (~2 ulp each); absolute error < 1e-6, far inside
 // the 1e-4 parity budget, and 2 MUFU + 3 FP32 ops per value instead of an IEEE division sequence.
-__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
-__device__ __forceinline__ float tanhf_(float v) { return fmaf(2.0f, sigmoidf_(2.0f * v), -1.0f); }
+// Written with the .ftz MUFU forms directly: __expf / __fdividef wrap the same instructions in denormal-range fix-ups
+// (FSETP + two predicated FMUL per ex2, a range test per division) that the saturating activations do not need --
+// e^-v below 1e-38 contributes nothing to 1 + e^-v, and rcp(inf) = 0 is the correct limit.  4 / 5 instructions per value.
+__device__ __forceinline__ float ex2_ftz_(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz_(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoidf_(float v) { return rcp_ftz_(1.0f + ex2_ftz_(-1.4426950408889634f * v)); }
+__device__ __forceinline__ float tanhf_(float v) {
+    return fmaf(2.0f, rcp_ftz_(1.0f + ex2_ftz_(-2.8853900817779268f * v)), -1.0f);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
