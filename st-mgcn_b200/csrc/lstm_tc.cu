@@ -299,7 +299,7 @@ __global__ void __launch_bounds__((FwdCfg<A_TMA>::kThreads), 1) lstm_cell_tc_ker
                     // gate tape: this warp's [32 rows][16 columns] piece goes through its staging tile (16-byte chunks
                     // XOR-swizzled with (row >> 1) & 3 == the TMA 64-byte swizzle, conflict-free for the lanes)
                     if (GATES_TMA) {                   // previous piece's tensor store must have read the tile
-                        if (lane == 0) bulk_wait_read0();
+                        if (lane == 0 && p.dbg_skip_hc != 2) bulk_wait_read0();
                     }
                     __syncwarp();
 #pragma unroll
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__((FwdCfg<A_TMA>::kThreads), 1) lstm_cell_tc_ker
                 if (GATES_TMA && p.hc_tma) {
                     // h / c through the same staging tile once the tape store has read it: the epilogue threads then
                     // issue no global stores at all, so the proxy fences (MEMBAR) have nothing outstanding to wait for
-                    if (lane == 0) bulk_wait_read0();
+                    if (lane == 0 && p.dbg_skip_hc != 2) bulk_wait_read0();
                     __syncwarp();
                     *reinterpret_cast<float4*>(stg + lane * 4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                     *reinterpret_cast<float4*>(stg + 128 + lane * 4) = make_float4(cn[0], cn[1], cn[2], cn[3]);
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__((FwdCfg<A_TMA>::kThreads), 1) lstm_cell_tc_ker
                             tma_store_2d(&p.c_map, smem_u32(stg + 128), unit0, (int)r0);
                         bulk_commit_group();
                     }
-                } else if (valid && !p.dbg_skip_hc) {
+                } else if (valid && p.dbg_skip_hc != 1) {
                     // h / c after the tape hand-off: the proxy fence above does not have to wait for these stores
                     *reinterpret_cast<float4*>(p.h_out + r * kHid + unit0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                     *reinterpret_cast<float4*>(p.c_out + ws_off(p.blocked_cs, r, unit0)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
@@ -1287,7 +1287,10 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
     p.gates_tma = 0;
     {
         static int skip = -1;
-        if (skip < 0) skip = env_flag("STMGCN_DBG_SKIP_HC", 0);
+        if (skip < 0) {          // 1: drop the h/c stores; 2: skip the staging-tile reuse waits (racy) -- timing experiments only
+            const char* e = getenv("STMGCN_DBG_SKIP_HC");
+            skip = e ? atoi(e) : 0;
+        }
         p.dbg_skip_hc = skip;
     }
     memset(&p.gates_map, 0, sizeof(p.gates_map));
@@ -1301,7 +1304,7 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
     {
         static int hc = -1;
         if (hc < 0) hc = env_flag("STMGCN_HC_TMA", 1);
-        if (hc && p.gates_tma && !p.dbg_skip_hc &&
+        if (hc && p.gates_tma && p.dbg_skip_hc != 1 &&
             make_tile_map(&p.h_map, h_out, rows, kHid, 4, 32, CU_TENSOR_MAP_SWIZZLE_NONE) &&
             (blocked_cs ? make_tile_map(&p.c_map, c_out, (int64_t)p.n_tiles * 8 * kTileM, 8, 4, 32, CU_TENSOR_MAP_SWIZZLE_NONE)
                         : make_tile_map(&p.c_map, c_out, rows, kHid, 4, 32, CU_TENSOR_MAP_SWIZZLE_NONE)))
