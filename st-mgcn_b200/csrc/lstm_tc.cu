@@ -8,13 +8,17 @@
 //           straight into the swizzled operand tiles of  [dx_below | dh_prev][128 x Kd] = dA[128 x 256] . Wp^T.
 //
 // CTA anatomy (persistent over 128-row tiles, 1 CTA / SM):
-//   epilogue warps : tcgen05.ld their TMEM lane quadrant -> registers -> math -> global
-//   loader warps   : HBM -> registers -> tf32 hi/lo split -> K-major 128B-swizzled smem operand tiles;
-//                    one thread also starts the bulk copies (TMA unit, UBLKCP) of the pre-swizzled hi/lo weight
-//                    images for the same k-block
+//   producer warp  : one thread issues every global->shared transfer through the TMA unit: tensor loads of raw A
+//                    tiles / gate slices (CUtensorMap built per launch), 4 KB bulk copies of tile-blocked workspace
+//                    slices, bulk copies (UBLKCP) of the pre-swizzled hi/lo weight images
+//   loader warps   : shared memory -> registers -> (backward: BPTT pointwise math) -> tf32 hi/lo split -> K-major
+//                    128B-swizzled operand tiles.  (Register-load variants, where these warps read HBM themselves,
+//                    remain as fallbacks: STMGCN_FWD_TMA=0 / STMGCN_BWD_TMA=0, row-major workspaces.)
 //   MMA warp       : one thread issues tcgen05.mma kind::tf32, 12 per 32-wide k-block (3 passes x 4 k-slices);
 //                    tcgen05.commit releases operand stages / publishes accumulators
-// Pipelines: operand stages (full/empty mbarriers) and two TMEM accumulators (tmem_full/tmem_empty).
+//   epilogue warps : tcgen05.ld their TMEM lane quadrant -> registers -> math -> forward: staging tile -> TMA tensor
+//                    stores (gate tape, h, c); backward: direct stores of [dx_below | dh_prev]
+// Pipelines: operand stages (full/empty mbarriers), raw slots (raw_full/raw_empty), two TMEM accumulators.
 #include "tc_pipeline.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -765,11 +769,11 @@ __global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_ker
 
 // =====================================================================================================
 // weight gradients:  dWp[kd x 256] += sum over (t, r) of [h_below_t | h_{t-1}][r, :]^T . dA_t[r, :]
-// M = kd index (padded to 128), N = 256 gate columns, K = rows.  Both operands are row-major in HBM (K is the slow
-// dimension); the loaders transpose them while writing shared memory -- lane <-> row, so the scalar stores of a
-// warp hit 32 different banks -- into the same K-major 128B-swizzled tiles the other kernels use.  (Setting the
-// MN-major bits of the tf32 instruction descriptor produced all-zero accumulators on B200 in our tests, so the
-// transposition is done in software.)  One TMEM accumulator lives for the whole kernel and is flushed with red.add.
+// M = kd index (padded to 128), N = 256 gate columns, K = rows.  Both operands are row-major in HBM, i.e. K is the slow
+// dimension: they are MN-major operands.  The loaders copy rows with coalesced float4 loads and store them as MN-major
+// atoms with the 32-byte-base 128B swizzle (layout type SWIZZLE_128B_BASE32B = 1, see mn32_offset in tc_common.cuh;
+// with the plain SWIZZLE_128B type and the MN-major descriptor bits the tf32 MMA returns zeros).  One TMEM
+// accumulator lives for the whole kernel and is flushed with red.add.
 // =====================================================================================================
 constexpr int kWgStages = 2;
 constexpr int kWgRows = 32;                                        // K per stage
@@ -845,7 +849,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
         static_assert(kNB >= 1, "loader mapping");
         const int ltid = tid;
         const int grp = ltid / kGT, gtid = ltid % kGT;
-        const int my_chunks_dummy = 0; (void)my_chunks_dummy;
         const int64_t my_chunks = (p.total_chunks - (int64_t)blockIdx.x + gridDim.x - 1) / gridDim.x;
         for (int64_t j = grp; j < my_chunks; j += kGroups) {
             const int64_t chunk = blockIdx.x + j * gridDim.x;

@@ -17,6 +17,9 @@ from . import _lib, ops
 from .graph import ChebSupports, supports_from_dense
 
 
+_BRANCH_STREAMS = {}
+
+
 def _graph_streams_enabled() -> bool:
     """One CUDA stream per graph branch in ``ST_MGCN.forward`` (``STMGCN_GRAPH_STREAMS=0`` runs them on one stream)."""
     return os.environ.get("STMGCN_GRAPH_STREAMS", "1") != "0"
@@ -202,8 +205,8 @@ class ST_MGCN(nn.Module):
         return ops.FuseOut.apply(self.fc.weight, self.fc.bias, *feats)
 
     def _branch_streams(self, device):
-        cache = getattr(self, "_streams", None)
-        if cache is None or cache[0] != device:
-            cache = (device, [torch.cuda.Stream(device=device) for _ in range(self.M)])
-            object.__setattr__(self, "_streams", cache)
-        return cache[1]
+        # process-wide cache (not a module attribute: streams must not end up in deepcopy / pickle of the model)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), self.M)
+        if key not in _BRANCH_STREAMS:
+            _BRANCH_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(self.M)]
+        return _BRANCH_STREAMS[key]

@@ -140,6 +140,49 @@ def test_lstm_weight_packing_roundtrip():
     assert torch.allclose(grads[2], ws[2] + ws[3])
 
 
+@pytest.mark.parametrize("rows", [128, 300, 1])
+def test_tile_blocked_layout_roundtrip_and_formula(rows):
+    """to_blocked / from_blocked are inverse, pad to whole 128-row tiles, and place element (r, u) where the kernels'
+    ws_off() expects it: (((r/128)*8 + u/8)*128 + r%128)*8 + u%8  (include/stmgcn_b200.h, stmgcn_lstm_step_bwd)."""
+    from stmgcn_b200 import ops
+    gen = torch.Generator().manual_seed(rows)
+    x = torch.randn(2, rows, 64, generator=gen)
+    blk = ops.to_blocked(x)
+    rp = ((rows + 127) // 128) * 128
+    assert blk.shape == (2, rp, 64) and blk.is_contiguous()
+    assert torch.equal(ops.from_blocked(blk, rows), x)
+    flat = blk.reshape(2, -1)
+    for r, u in [(0, 0), (rows - 1, 63), (rows // 2, 9), (min(rows - 1, 127), 8)]:
+        off = (((r // 128) * 8 + u // 8) * 128 + r % 128) * 8 + u % 8
+        assert float(flat[1, off]) == float(x[1, r, u])
+    if rp != rows:                                           # padding rows are zero
+        back = ops.from_blocked(blk, rp)
+        assert float(back[:, rows:].abs().max()) == 0.0
+
+
+def test_environment_switches_in_readme_exist_in_the_sources():
+    """Every STMGCN_* switch the README advertises is read somewhere in the product code (and vice versa for the
+    switches that change which kernel runs)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    readme = open(os.path.join(root, "README.md")).read()
+    advertised = set(re.findall(r"`(STMGCN_[A-Z_0-9]+)=", readme))
+    src = ""
+    for d, _, files in os.walk(os.path.join(root, "st-mgcn_b200")):
+        if os.sep + "build" in d or "__pycache__" in d:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src += open(os.path.join(d, f)).read()
+    used = set(re.findall(r'"(STMGCN_[A-Z_0-9]+)"', src))
+    assert advertised, "README lists no switches"
+    missing = advertised - used
+    assert not missing, f"README advertises switches the code never reads: {sorted(missing)}"
+    kernel_switches = {s for s in used if not s.startswith(("STMGCN_DBG", "STMGCN_TC_PROFILE"))}
+    undocumented = kernel_switches - advertised
+    assert not undocumented, f"switches missing from README: {sorted(undocumented)}"
+
+
 def test_synthetic_workloads_match_survey_table():
     from stmgcn_b200 import synth
     w = synth.WORKLOADS["cfg3"]
