@@ -56,13 +56,13 @@ def test_product_code_never_imports_the_oracle():
         assert not pat.search(open(path).read()), f"{path} imports the oracle"
 
 
-@pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref"])
+@pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref", "cfg3_small_ref"])
 def test_state_dict_surface_and_same_seed_init(name):
     """Same ctor keywords as Main.py:62-63; state_dict keys/shapes equal the reference's; constructing under
     the same seed reproduces the reference's parameters bit for bit (parameter creation order preserved)."""
     import STMGCN
     meta, params, _, _, _, _ = load_golden(name)
-    seed = 0 if name == "cfg1_ref" else 1
+    seed = {"cfg1_ref": 0, "ragged_ref": 1, "cfg3_small_ref": 2}[name]
     torch.manual_seed(seed)
     model = STMGCN.ST_MGCN(M=meta["m"], seq_len=meta["t"], n_nodes=meta["n"], input_dim=meta["c"],
                            lstm_hidden_dim=meta["hid"], lstm_num_layers=meta["layers"], gcn_hidden_dim=meta["gcn_hid"],
@@ -82,7 +82,7 @@ def test_state_dict_surface_and_same_seed_init(name):
         STMGCN.ST_MGCN.get_support_K({"kernel_type": "nope", "K": 1})
 
 
-@pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref"])
+@pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref", "cfg3_small_ref"])
 def test_adj_preprocessor_equals_reference_supports(name):
     import GCN
     meta, _, _, supports, adjs, _ = load_golden(name)

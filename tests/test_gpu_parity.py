@@ -62,7 +62,7 @@ def test_spmm_step(n, f, transpose):
     assert_close(ud.cpu().numpy(), 2.0 * (op.astype(np.float64) @ x) - z + u, "spmm in-place", 1e-5)
 
 
-@pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref"])
+@pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref", "cfg3_small_ref"])
 def test_model_matches_reference_golden(name):
     """Forward output, loss and EVERY parameter gradient vs vectors produced by the unmodified reference."""
     meta, params, grads, supports, _, blob = load_golden(name)

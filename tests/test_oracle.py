@@ -15,7 +15,7 @@ from helpers import TOL, assert_close, load_golden
 REF = "/root/reference"
 
 
-@pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref"])
+@pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref", "cfg3_small_ref"])
 def test_dense_oracle_matches_reference_golden(name):
     meta, params, grads, supports, adjs, blob = load_golden(name)
     x, y = torch.from_numpy(blob["x"]), torch.from_numpy(blob["y"])
@@ -29,7 +29,7 @@ def test_dense_oracle_matches_reference_golden(name):
         assert_close(O.chebyshev_supports_dense(a, meta["k"]).numpy(), s.numpy(), "supports", 1e-6)
 
 
-@pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref"])
+@pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref", "cfg3_small_ref"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_sparse_oracle_matches_reference_golden(name, dtype):
     """Recurrence-on-features + hand-written backward == the reference's dense forward + autograd."""
