@@ -80,6 +80,23 @@ def test_known_answer_chebyshev_eigenvector():
         assert np.allclose(st[k].ravel(), np.cos(k * np.arccos(lam)) * v.numpy(), atol=1e-12)
 
 
+def test_known_answer_ring_graph_spectrum():
+    """Ring graph: the normalised adjacency has eigenvalues cos(2 pi j / n), so the rescaled Laplacian supports[1]
+    (lambda_max = 2, GCN.py:86-93) has spectrum -cos(2 pi j / n) and supports[k] has spectrum T_k of it."""
+    n, k_ord = 16, 3
+    adj = torch.zeros(n, n, dtype=torch.float64)
+    idx = torch.arange(n)
+    adj[idx, (idx + 1) % n] = 1
+    adj[(idx + 1) % n, idx] = 1
+    sup = O.chebyshev_supports_dense(adj, k_ord)
+    lam = np.sort(-np.cos(2 * np.pi * np.arange(n) / n))
+    got = np.sort(np.linalg.eigvalsh(sup[1].numpy()))
+    assert np.allclose(got, lam, atol=1e-12)
+    for k in range(k_ord + 1):
+        want = np.sort(np.cos(k * np.arccos(np.clip(lam, -1, 1))))
+        assert np.allclose(np.sort(np.linalg.eigvalsh(sup[k].numpy())), want, atol=1e-10)
+
+
 def test_known_answer_order_zero_gcn_is_a_linear_layer():
     x = torch.randn(3, 9, 4)
     w, b = torch.randn(4, 5), torch.randn(5)
