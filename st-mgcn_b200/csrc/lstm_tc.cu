@@ -368,6 +368,280 @@ __global__ void __launch_bounds__((FwdCfg<A_TMA>::kThreads), 1) lstm_cell_tc_ker
 }
 
 // =====================================================================================================
+// forward cell, N-split variant with RESIDENT weight halves  --  EXPERIMENTAL, opt-in (STMGCN_FWD_NSPLIT=1)
+// Written at the end of round 1 from the profile of lstm_cell_tc_kernel; it compiles but
+// has NOT been run on hardware yet, so nothing selects it by default and no test depends on it.
+//
+// The gate columns are unit-interleaved (col = 4*unit + gate), so columns [128h, 128h+128) are a self-contained half
+// (units 32h .. 32h+31).  CTA c owns half h = c & 1 for the whole launch: the hi/lo weight images of its half for all
+// k-blocks (4 x 32 KB) are loaded ONCE and stay in shared memory; only the 16 KB raw A tiles stream through two stages
+// (TMA tensor load into the hi tile, split in place); four 128-column TMEM accumulators decouple the MMA warp from the
+// epilogue.  CTAs 2i and 2i+1 walk the same tile sequence, so the second read of an A tile hits L2.
+// =====================================================================================================
+constexpr int kNsN = 128;                                         // gate columns per CTA
+constexpr int kNsStages = 2;
+constexpr int kNsAStage = 2 * kABytes;                            // 32 KB: A hi | A lo
+constexpr int kNsBHalf = kNsN * kKB * 4;                          // 16 KB: [128 n][32 k] hi or lo of one k-block
+constexpr int kNsBkb = 2 * kNsBHalf;                              // 32 KB per k-block: hi | lo
+constexpr int kNsMaxKb = 4;
+constexpr int kNsAccs = 4;
+constexpr int kNsEpiWarps = 16;
+constexpr int kNsSplitWarps = 8;
+constexpr int kNsThreads = (kNsEpiWarps + kNsSplitWarps + 2) * 32;
+struct NsTail {
+    float bias[kGateCols];
+    uint64_t a_full[kNsStages];
+    uint64_t full[kNsStages];
+    uint64_t empty[kNsStages];
+    uint64_t b_full;
+    uint64_t tmem_full[kNsAccs];
+    uint64_t tmem_empty[kNsAccs];
+    uint32_t tmem_base;
+};
+constexpr size_t kNsSmem = 1024 + (size_t)kNsMaxKb * kNsBkb + (size_t)kNsStages * kNsAStage +
+                           (size_t)kNsEpiWarps * kStagingBytes + sizeof(NsTail);
+static_assert(kNsSmem <= 232448, "N-split forward kernel exceeds the 227 KB shared-memory limit");
+
+__global__ void __launch_bounds__(kNsThreads, 1) lstm_cell_nsplit_kernel(const __grid_constant__ CellParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* bres = smem;                                          // resident weight half: nkb x [hi 16 KB | lo 16 KB]
+    uint8_t* stages = bres + (size_t)kNsMaxKb * kNsBkb;
+    uint8_t* staging = stages + (size_t)kNsStages * kNsAStage;
+    NsTail* tail = (NsTail*)(staging + (size_t)kNsEpiWarps * kStagingBytes);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    constexpr int kMmaWarp = kNsEpiWarps + kNsSplitWarps;
+    constexpr int kSplitters = kNsSplitWarps * 32;
+    const int half = blockIdx.x & 1;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;     // host launches an even grid
+    const int my_tiles = pair < p.n_tiles ? (p.n_tiles - pair + npairs - 1) / npairs : 0;
+
+    pdl_launch_dependents();
+    if (tid == 0) {
+        for (int s = 0; s < kNsStages; ++s) {
+            mbar_init(&tail->a_full[s], 1);
+            mbar_init(&tail->full[s], kSplitters);
+            mbar_init(&tail->empty[s], 1);
+        }
+        mbar_init(&tail->b_full, 1);
+        for (int a = 0; a < kNsAccs; ++a) {
+            mbar_init(&tail->tmem_full[a], 1);
+            mbar_init(&tail->tmem_empty[a], kNsEpiWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, 512);
+    for (int i = tid; i < kGateCols; i += kNsThreads) tail->bias[i] = p.bias ? p.bias[i] : 0.f;
+    pdl_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+
+    if (warp >= kNsEpiWarps && warp < kMmaWarp) {
+        // ===================== splitters: raw A tile (in the stage's hi tile) -> tf32 hi in place + lo =====================
+        const int gtid = tid - kNsEpiWarps * 32;
+        constexpr int kPer = 1024 / kSplitters;                    // 4 float4 per thread per k-block
+        const int c = gtid & 7, rsub = gtid >> 3;                  // rows rsub + 32*i, 16-byte chunk c of the 128-byte row
+        const int total = my_tiles * p.nkb;
+        for (int j = 0; j < total; ++j) {
+            const int tile = pair + (j / p.nkb) * npairs, kb = j % p.nkb;
+            const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
+            const bool aux_blk = p.aux && kb == 2;
+            const bool from_tma = !aux_blk && seg != nullptr;
+            const int s = j % kNsStages;
+            const uint32_t ph = (j / kNsStages) & 1;
+            uint8_t* st = stages + (size_t)s * kNsAStage;
+            mbar_wait_raw(&tail->a_full[s], ph);
+            float4 buf[kPer];
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                const int row = rsub + (kSplitters / 8) * i;
+                const int64_t r = (int64_t)tile * kTileM + row;
+                if (from_tma) {
+                    buf[i] = *reinterpret_cast<const float4*>(st + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4));
+                } else if (aux_blk) {                              // [x*s (C cols) | 1 | 0 ...]
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (c < 2 && r < p.rows) {
+                        const float sv = p.sg[(r % p.b_inner) * p.t_len + p.t];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int col = 4 * c + jj;
+                            if (col < p.c_in) v[jj] = p.xo[(r * p.t_len + p.t) * p.c_in + col] * sv;
+                            else if (col == p.c_in) v[jj] = 1.0f;
+                        }
+                    }
+                    buf[i] = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+                    buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);     // absent segment (h_{-1} = 0)
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                const int row = rsub + (kSplitters / 8) * i;
+                split_store(st, (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4), buf[i]);   // hi at st, lo at st + kABytes
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&tail->full[s]);
+        }
+    } else if (warp == kMmaWarp) {
+        // ===================== MMA issuer: A from the stage, B from the resident half =====================
+        constexpr uint32_t idesc = idesc_tf32(kTileM, kNsN);
+        mbar_wait_raw(&tail->b_full, 0);
+        tc_fence_after();
+        uint32_t it = 0;
+        for (int item = 0; item < my_tiles; ++item) {
+            const int a = item % kNsAccs;
+            const uint32_t aph = (uint32_t)(item / kNsAccs) & 1;
+            mbar_wait_raw(&tail->tmem_empty[a], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)a * kNsN;
+            for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+                const int s = it % kNsStages;
+                const uint32_t ph = (it / kNsStages) & 1;
+                mbar_wait_raw(&tail->full[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = smem_u32(stages + (size_t)s * kNsAStage);
+                    const uint32_t bb = smem_u32(bres + (size_t)kb * kNsBkb);
+                    const uint64_t a_hi = smem_desc_k_sw128(st);
+                    const uint64_t a_lo = smem_desc_k_sw128(st + kABytes);
+                    const uint64_t b_hi = smem_desc_k_sw128(bb);
+                    const uint64_t b_lo = smem_desc_k_sw128(bb + kNsBHalf);
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint64_t da = (pass == 1) ? a_lo : a_hi;
+                        const uint64_t db = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+                        for (int k = 0; k < kKB / 8; ++k)
+                            mma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                     (kb > 0 || pass > 0 || k > 0) ? 1u : 0u);
+                    }
+                    mma_commit(&tail->empty[s]);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) mma_commit(&tail->tmem_full[a]);
+            __syncwarp();
+        }
+    } else if (warp == kMmaWarp + 1) {
+        // ===================== producer: resident weight half once, then one raw A tile per freed stage =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&tail->b_full, (uint32_t)p.nkb * kNsBkb);
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const float* img = p.wimg + (size_t)kb * (2 * kFwdBBytes / 4);              // [hi 256 x 32 | lo 256 x 32]
+                bulk_g2s(bres + (size_t)kb * kNsBkb, img + (size_t)half * (kNsBHalf / 4), kNsBHalf, &tail->b_full);
+                bulk_g2s(bres + (size_t)kb * kNsBkb + kNsBHalf, img + kFwdBBytes / 4 + (size_t)half * (kNsBHalf / 4), kNsBHalf,
+                         &tail->b_full);
+            }
+            const int total = my_tiles * p.nkb;
+            for (int j = 0; j < total; ++j) {
+                const int tile = pair + (j / p.nkb) * npairs, kb = j % p.nkb;
+                const int s = j % kNsStages;
+                const uint32_t ph = (j / kNsStages) & 1;
+                mbar_wait_raw(&tail->empty[s], ph ^ 1);
+                const float* seg = (kb >> 1) ? p.seg1 : p.seg0;
+                if (!(p.aux && kb == 2) && seg != nullptr) {
+                    mbar_arrive_expect_tx(&tail->a_full[s], kABytes);
+                    tma_load_2d(stages + (size_t)s * kNsAStage, (kb >> 1) ? &p.seg1_map : &p.seg0_map, (kb & 1) * kKB,
+                                tile * kTileM, &tail->a_full[s]);
+                } else {
+                    mbar_arrive(&tail->a_full[s]);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: LSTM cell on this CTA's 32 units =====================
+        // 16 warps: TMEM lane quadrant q = warp & 3, column quarter part = warp >> 2 (32 of the 128 columns = 8 units),
+        // processed as two 16-column pieces of 4 units each
+        const int q = warp & 3, part = warp >> 2;
+        float* stg = reinterpret_cast<float*>(staging + (size_t)warp * kStagingBytes);
+        const int ubase = 32 * half + 8 * part;                    // first unit of this warp
+        float4 cpv[2];
+        auto fetch_cprev = [&](int tile_n) {
+            const int64_t rn = (int64_t)tile_n * kTileM + q * 32 + lane;
+            const bool okn = p.c_prev != nullptr && tile_n < p.n_tiles && rn < p.rows;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                cpv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (okn) cpv[j] = *reinterpret_cast<const float4*>(p.c_prev + ws_off(p.blocked_cs, rn, ubase + 4 * j));
+            }
+        };
+        fetch_cprev(pair);
+        for (int item = 0; item < my_tiles; ++item) {
+            const int tile = pair + item * npairs;
+            const int a = item % kNsAccs;
+            const uint32_t aph = (uint32_t)(item / kNsAccs) & 1;
+            const int64_t r0 = (int64_t)tile * kTileM + q * 32;
+            mbar_wait_raw(&tail->tmem_full[a], aph);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * kNsN + (uint32_t)part * 32;
+#pragma unroll
+            for (int pc = 0; pc < 2; ++pc) {
+                uint32_t v[16];
+                tmem_ld16(t_row + pc * 16, v);
+                const int unit0 = ubase + pc * 4;
+                const float cp[4] = {cpv[pc].x, cpv[pc].y, cpv[pc].z, cpv[pc].w};
+                tmem_ld_wait();
+                float hn[4], cn[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[4 * (unit0 + u)]);
+                    const float gi = sigmoidf_(__uint_as_float(v[4 * u + 0]) + bv.x);
+                    const float gf = sigmoidf_(__uint_as_float(v[4 * u + 1]) + bv.y);
+                    const float gg = tanhf_(__uint_as_float(v[4 * u + 2]) + bv.z);
+                    const float go = sigmoidf_(__uint_as_float(v[4 * u + 3]) + bv.w);
+                    cn[u] = fmaf(gf, cp[u], gi * gg);
+                    hn[u] = go * tanhf_(cn[u]);
+                    v[4 * u + 0] = __float_as_uint(gi);
+                    v[4 * u + 1] = __float_as_uint(gf);
+                    v[4 * u + 2] = __float_as_uint(gg);
+                    v[4 * u + 3] = __float_as_uint(go);
+                }
+                if (p.gates_out != nullptr) {
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        *reinterpret_cast<uint4*>(stg + lane * 16 + ((u ^ ((lane >> 1) & 3)) << 2)) =
+                            make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&p.gates_map, smem_u32(stg), 4 * unit0, (int)r0);
+                        bulk_commit_group();
+                    }
+                }
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+                *reinterpret_cast<float4*>(stg + lane * 4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                *reinterpret_cast<float4*>(stg + 128 + lane * 4) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&p.h_map, smem_u32(stg), unit0, (int)r0);
+                    if (p.blocked_cs)
+                        tma_store_2d(&p.c_map, smem_u32(stg + 128), unit0 & 7, (tile * 8 + (unit0 >> 3)) * kTileM + q * 32);
+                    else
+                        tma_store_2d(&p.c_map, smem_u32(stg + 128), unit0, (int)r0);
+                    bulk_commit_group();
+                }
+            }
+            fetch_cprev(tile + npairs);
+            tc_fence_before();
+            mbar_arrive(&tail->tmem_empty[a]);
+        }
+        if (lane == 0) bulk_wait0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================
 // backward: pointwise dA in the loader + data GEMM  [dx_below | dh_prev] = dA . Wp^T
 // =====================================================================================================
 constexpr int kBwdEpiWarps = 4;
@@ -1319,6 +1593,20 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
     bool a_tma = fwd_tma_enabled() != 0;
     if (a_tma && seg0) a_tma = make_tile_map(&p.seg0_map, seg0, rows, kHid, kKB, kTileM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (a_tma && seg1) a_tma = make_tile_map(&p.seg1_map, seg1, rows, kHid, kKB, kTileM, CU_TENSOR_MAP_SWIZZLE_128B);
+    static int nsplit = -1;               // EXPERIMENTAL resident-weight N-split kernel (not yet validated on hardware)
+    if (nsplit < 0) nsplit = env_flag("STMGCN_FWD_NSPLIT", 0);
+    if (nsplit && p.gates_tma && p.hc_tma && a_tma && sm_count() >= 2) {
+        static bool ns_attr = false;
+        if (!ns_attr) {
+            STMGCN_CUDA(cudaFuncSetAttribute(lstm_cell_nsplit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNsSmem));
+            ns_attr = true;
+        }
+        int pairs = sm_count() / 2;
+        if (pairs > p.n_tiles) pairs = p.n_tiles;
+        STMGCN_CUDA(launch_pdl(lstm_cell_nsplit_kernel, 2 * pairs, kNsThreads, kNsSmem, st, p));
+        count_launch();
+        return check_launch("lstm_cell_nsplit");
+    }
     if (p.gates_tma) {
         if (a_tma) STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<true, true>, grid, FwdCfg<true>::kThreads, kFwdSmem, st, p));
         else STMGCN_CUDA(launch_pdl(lstm_cell_tc_kernel<true, false>, grid, FwdCfg<false>::kThreads, kFwdSmem, st, p));
