@@ -368,9 +368,10 @@ __global__ void __launch_bounds__((FwdCfg<A_TMA>::kThreads), 1) lstm_cell_tc_ker
 }
 
 // =====================================================================================================
-// forward cell, N-split variant with RESIDENT weight halves  --  EXPERIMENTAL, opt-in (STMGCN_FWD_NSPLIT=1)
-// Written at the end of round 1 from the profile of lstm_cell_tc_kernel; it compiles but
-// has NOT been run on hardware yet, so nothing selects it by default and no test depends on it.
+// forward cell, N-split variant with RESIDENT weight halves  --  opt-in (STMGCN_FWD_NSPLIT=1), kept for study
+// Written at the end of round 1 from the profile of lstm_cell_tc_kernel.  It passes the
+// golden and TC-vs-FFMA parity tests but is 18 % SLOWER than lstm_cell_tc_kernel (6.39 vs 5.4 ms per branch forward at
+// cfg3): every A tile is split to tf32 hi/lo by two CTAs, and that costs more than the resident weights gain.
 //
 // The gate columns are unit-interleaved (col = 4*unit + gate), so columns [128h, 128h+128) are a self-contained half
 // (units 32h .. 32h+31).  CTA c owns half h = c & 1 for the whole launch: the hi/lo weight images of its half for all
@@ -1593,7 +1594,7 @@ int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int 
     bool a_tma = fwd_tma_enabled() != 0;
     if (a_tma && seg0) a_tma = make_tile_map(&p.seg0_map, seg0, rows, kHid, kKB, kTileM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (a_tma && seg1) a_tma = make_tile_map(&p.seg1_map, seg1, rows, kHid, kKB, kTileM, CU_TENSOR_MAP_SWIZZLE_128B);
-    static int nsplit = -1;               // EXPERIMENTAL resident-weight N-split kernel (not yet validated on hardware)
+    static int nsplit = -1;               // resident-weight N-split kernel: correct but measured slower, opt-in
     if (nsplit < 0) nsplit = env_flag("STMGCN_FWD_NSPLIT", 0);
     if (nsplit && p.gates_tma && p.hc_tma && a_tma && sm_count() >= 2) {
         static bool ns_attr = false;
