@@ -7,8 +7,8 @@ Contract (driver): prints ONE JSON line on rank 0.  ``value`` = whole-job region
 resident in HBM; ``e2e`` = the same metric through the public module API with HOST (pinned) inputs, the
 host->device copies and a device->host read of the loss inside the timed region; ``roofline`` = the
 Chebyshev SpMM (the forward's 18 recurrence launches at cfg3) timed alone with CUDA events against the
-measured HBM peak; ``cpu_baseline`` = the oracle port (dense supports + nn.LSTM, what the reference executes)
-on this box's host cores on a bounded sample.  ``--impl reference`` times only that CPU path.
+measured HBM peak; ``cpu_baseline`` = the UNMODIFIED reference modules (``baseline/_ref``, staged by build(); the
+oracle port if absent) on this box's host cores on a bounded sample.  ``--impl reference`` times only that CPU path.
 
 Default workload: cfg3 = BASELINE.json configs[2] (4096 regions, 3 graphs, K=3, seq_len=12, batch 64 per
 GPU, fp32) -- the configuration BASELINE.json's metric quotes the SpMM HBM figure on, and the largest fp32
@@ -126,30 +126,87 @@ def spmm_algorithmic_bytes(n, nnz, f_total, k_order, elem=4):
 # ---------------------------------------------------------------------------------------------------
 # reference arm: the oracle port (dense supports + nn.LSTM, the reference's algorithm) on host cores
 # ---------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(REPO, "baseline", "_ref")
+
+
+def _reference_modules():
+    """The UNMODIFIED reference's ``GCN`` / ``STMGCN`` modules from ``baseline/_ref`` (staged by
+    ``__graft_entry__.build()``), imported under private names so they can never shadow the repo's drop-in modules.
+    Returns None when the directory was not staged (then the oracle port is timed instead)."""
+    if not os.path.exists(os.path.join(REF_DIR, "STMGCN.py")):
+        return None
+    import importlib.util
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(f"_stmgcn_ref_{name}", os.path.join(REF_DIR, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    ref_gcn = load("GCN")
+    saved = sys.modules.get("GCN")
+    sys.modules["GCN"] = ref_gcn                 # STMGCN.py:4 does `from GCN import GCN`: must resolve to the reference's
+    try:
+        ref_stmgcn = load("STMGCN")
+    finally:
+        if saved is not None:
+            sys.modules["GCN"] = saved
+        else:
+            sys.modules.pop("GCN", None)
+    return ref_gcn, ref_stmgcn
+
+
 def cpu_reference_run(w, steps, warmup, sample_batch=None, log=None, step_budget_s=6.0):
-    """Time the oracle port (dense supports + nn.LSTM: what the reference executes) on the host cores.
+    """Time the reference's CPU implementation of the path on the host cores.
+
+    kind "reference": the unmodified reference modules from ``baseline/_ref`` -- ``Adj_Preprocessor.process`` (dense
+    supports, GCN.py:57-97), ``ST_MGCN.forward`` (STMGCN.py:100-119), ``nn.MSELoss``, ``backward`` -- exactly the step of
+    ``Model_Trainer.py:35-41`` without the optimizer.  kind "port": the oracle's dense restatement (same algorithm, same
+    torch ops) when ``baseline/_ref`` is absent.
 
     Thread count: "all the host threads it can use" is calibrated, not assumed -- on the GPU boxes os.cpu_count()
     reports 128 logical CPUs but running 128 intra-op threads is ~50x SLOWER than 16-32 (measured: 64 s vs 1.1 s for a
     2-window step), so candidates are tried smallest-first on a 1-window step and the fastest is used; `cores` in the
     result is the number of threads actually used.  The sample batch is then sized to ~step_budget_s per step."""
     import torch
-    sys.path.insert(0, os.path.join(REPO, "oracle"))
-    import stmgcn_oracle as O
+    from torch import nn
     from stmgcn_b200 import synth
     ncpu = os.cpu_count() or 1
     torch.set_num_threads(min(ncpu, 16))
+    ref = _reference_modules()
     t0 = time.time()
     adjs = synth.make_adjacency_list(w)
-    sups = [O.chebyshev_supports_dense(a, w.cheb_order) for a in adjs]      # GCN.py:57-97 (dense, once)
-    prep_s = time.time() - t0
-    params = O.init_params(w.n_graphs, w.seq_len, w.input_dim, w.lstm_hidden, w.lstm_layers, w.gcn_hidden,
-                           w.n_supports, seed=0)
+    if ref is not None:
+        ref_gcn, ref_stmgcn = ref
+        kind = "reference"
+        pre = ref_gcn.Adj_Preprocessor("chebyshev", w.cheb_order)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):        # GCN.py:119-121 prints its lambda_max fallback notice
+            sups = [pre.process(a) for a in adjs]              # GCN.py:57-97 (dense polynomials, once)
+        torch.manual_seed(0)
+        model = ref_stmgcn.ST_MGCN(**synth.model_kwargs(w))
+        crit = nn.MSELoss(reduction="mean")
 
-    def one_step(x, y):
-        t1 = time.time()
-        O.dense_loss_and_grads(params, x, y, sups, relu=True, lstm=O.lstm_library)
-        return time.time() - t1
+        def one_step(x, y):
+            t1 = time.time()
+            model.zero_grad(set_to_none=True)
+            loss = crit(model(obs_seq=x, sta_adj_list=sups), y)          # Model_Trainer.py:35,38
+            loss.backward()                                               # Model_Trainer.py:41
+            return time.time() - t1
+    else:
+        kind = "port"
+        sys.path.insert(0, os.path.join(REPO, "oracle"))
+        import stmgcn_oracle as O
+        sups = [O.chebyshev_supports_dense(a, w.cheb_order) for a in adjs]
+        params = O.init_params(w.n_graphs, w.seq_len, w.input_dim, w.lstm_hidden, w.lstm_layers, w.gcn_hidden,
+                               w.n_supports, seed=0)
+
+        def one_step(x, y):
+            t1 = time.time()
+            O.dense_loss_and_grads(params, x, y, sups, relu=True, lstm=O.lstm_library)
+            return time.time() - t1
+    prep_s = time.time() - t0
 
     x1, y1 = synth.make_inputs(w, seed=0, batch=1)
     one_step(x1, y1)                                           # warm the allocator / oneDNN primitives
@@ -178,14 +235,17 @@ def cpu_reference_run(w, steps, warmup, sample_batch=None, log=None, step_budget
     mean = sum(times) / len(times)
     value = sample_batch * w.n_regions * w.seq_len / mean
     try:
-        model = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+        model_name = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
     except Exception:
-        model = "unknown"
-    return dict(value=value, unit=UNIT, cores=best_c, kind="port",
+        model_name = "unknown"
+    what = ("the UNMODIFIED reference modules (baseline/_ref: Adj_Preprocessor.process dense supports, ST_MGCN.forward, "
+            "MSELoss, backward)" if kind == "reference" else
+            "the oracle port (dense supports + nn.LSTM, as the reference executes; baseline/_ref not staged)")
+    return dict(value=value, unit=UNIT, cores=best_c, kind=kind,
                 sample=f"{w.name} shapes with batch {sample_batch} (of {w.batch}), {steps} timed step(s) after "
-                       f"{warmup} warm-up, fwd+MSE+bwd, dense supports + nn.LSTM as the reference executes, "
+                       f"{warmup} warm-up, fwd+MSE+bwd through {what}, "
                        f"{best_c} intra-op threads (calibrated; {ncpu} logical CPUs visible); support preprocessing "
-                       f"{prep_s:.1f}s excluded; cpu '{model}'"), mean
+                       f"{prep_s:.1f}s excluded; cpu '{model_name}'"), mean
 
 
 def run_reference(args, w):

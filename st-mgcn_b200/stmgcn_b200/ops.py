@@ -222,8 +222,14 @@ class TemporalPool(torch.autograd.Function):
         if w.shape[1] != t:
             raise ValueError("temporal GCN must map seq_len -> seq_len")
         s = build_stack(sset, x)
-        pool = torch.zeros((b, t), device=x.device, dtype=torch.float32)
-        out = _proj_fwd(s, w, bias_c, act, pool, b)
+        if sset.mode == "cheb":
+            # s[0] IS x (T_0 = I): the kernel's fused pooling adds the residual from the stack's first segment
+            pool = torch.zeros((b, t), device=x.device, dtype=torch.float32)
+            out = _proj_fwd(s, w, bias_c, act, pool, b)
+        else:
+            # generic supports (localpool, hand-made stacks): s[0] = A_0 x is NOT the residual of STMGCN.py:41
+            out = _proj_fwd(s, w, bias_c, act, None, b)
+            pool = (x + out).sum(dim=0)
         ctx.act, ctx.has_bias = act, bias is not None
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(s, w, out)
