@@ -167,6 +167,49 @@ int32_t stmgcn_lstm_wgrad(int32_t layer, int32_t t_len, int32_t n_layers, int64_
                           const float* h0, const float* hs, const float* gates_da, float* dwp,
                           int32_t use_tc, void* stream);
 
+/* ---- K3b, second generation (H = 64 only): bf16-plane tensor-core LSTM without a gate tape ---------------------
+ * Same arithmetic contract as stmgcn_lstm_step_fwd/_bwd/_wgrad (STMGCN.py:44, :47-50; nn.LSTM semantics, fp32 state and
+ * accumulation), different tape:
+ *   hp : (L, T, P, R, 64) bf16 -- every hidden state as P planes; P = 2: hi = bf16(h), lo = bf16(h - hi) (3-pass
+ *        "3xBF16" products, ~2^-18 operand error: fp32-grade, the 1e-4 parity bar holds with >10x margin);
+ *        P = 1: hi only, single-pass bf16 products (the arithmetic of the bf16-quoted BASELINE configs).
+ *   cs : (L, T, ceil(R/128)*128, 64) fp32, tile-blocked (element (r,u) at (((r/128)*8 + u/8)*128 + r%128)*8 + u%8).
+ * No gate tape: the backward recomputes the gates from hp (which it needs anyway for the weight gradients).
+ * stmgcn_lstm16_pack turns one layer's nn.LSTM parameters (native layout: w_ih (256, in), w_hh (256, 64), b_ih, b_hh
+ * (256), gate order i,f,g,o) into the resident operand image wimg (layer 0: 64 KB, layers > 0: 128 KB; tiles
+ * [(segment, plane)] of [256 gate-interleaved columns][64 k] bf16, 128-byte swizzled), bias (256) = b_ih + b_hh
+ * gate-interleaved (col = 4*unit + gate) and, for layer 0, wih_t (C, 256) = W_ih^T gate-interleaved. */
+int32_t stmgcn_lstm16_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int32_t layer,
+                           int32_t c_in, void* wimg, float* bias, float* wih_t, void* stream);
+/* One timestep, all layers.  h0p: (L, P, R, 64) bf16 planes of the initial hidden state and c0: (L, R_pad, 64) fp32
+ * tile-blocked, or both NULL (zeros, STMGCN.py:53-57).  At t = T-1 the fp32 hidden state is also written: every layer
+ * into h_n (L, R, 64) when h_n != NULL, else only the top layer into h_top (R, 64) -- the (N,B,H) operand of the
+ * spatial GCN (STMGCN.py:50, :114).  C <= 4. */
+int32_t stmgcn_lstm16_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t c_in,
+                               int64_t b_inner, int32_t planes, const float* xo, const float* s_gate,
+                               const void* const* wimg, const float* const* bias, const float* wih_t,
+                               const void* h0p, const float* c0, void* hp, float* cs, float* h_top, float* h_n,
+                               void* stream);
+
+/* grid (CTAs) the lstm16 kernels use for `rows` rows: the number of weight-gradient scratch slices per layer */
+int32_t stmgcn_lstm16_grid(int64_t rows);
+/* BPTT step t (call t = T-1 .. 0), all layers top-down: recomputes the gates from hp, forms dA, accumulates the weight
+ * gradients and propagates [dx_below | dh_prev] -- one fused kernel per layer.  Workspaces (tile-blocked, R_pad rows):
+ * d_top (R_pad,64): gradient of the top layer's last hidden state; dh_rec, dc: (L,R_pad,64); dx_work: (R_pad,64); none needs
+ * initialisation.  Accumulates (+=; caller zeroes): d_s (B,T), dbp[l] (256, gate-interleaved).  dw_scratch:
+ * (L, stmgcn_lstm16_grid(rows), 128*256) floats, no initialisation needed (the call with t = T-1 writes it). */
+int32_t stmgcn_lstm16_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t c_in,
+                               int64_t b_inner, int32_t planes, const float* xo, const float* s_gate,
+                               const void* const* wimg, const float* const* bias, const float* wih_t,
+                               const void* h0p, const float* c0, const void* hp, const float* cs,
+                               const float* d_top, float* dh_rec, float* dc, float* dx_work, float* d_s,
+                               float* const* dbp, float* dw_scratch, void* stream);
+/* After all stmgcn_lstm16_step_bwd calls: sum layer `layer`'s scratch slices into nn.LSTM-native gradients
+ * d_w_ih (256, in), d_w_hh (256, 64), d_b_ih = d_b_hh (256) (overwritten, not accumulated). */
+int32_t stmgcn_lstm16_wgrad_reduce(int32_t layer, int32_t c_in, int32_t n_slices, const float* slices,
+                                   const float* dbp, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh,
+                                   void* stream);
+
 /* ---- fusion over graphs + output FC (STMGCN.py:116-118) ------------------------------------------
  * feat = sum_m g[m] (each (R, G) node-major); y[b, n, c] = feat[n*B+b, :] . fcw[c, :] + fcb[c]. */
 int32_t stmgcn_fuse_out_fwd(const float* const* g, int32_t m, int64_t n, int64_t b, int32_t gdim,

@@ -1,0 +1,65 @@
+"""Reference losses for bench.py's loss check.  TEST INFRASTRUCTURE (runs in the build container, CPU only).
+
+bench.py times the hot path on synthetic inputs that are a pure function of (workload, batch, rank): the model is
+``torch.manual_seed(0); ST_MGCN(**synth.model_kwargs(w))`` and rank r feeds ``synth.make_inputs(w, seed=100 + r)``.
+For those inputs the MSE loss of the first step is a constant; this script computes it with the sparse oracle
+(``SparseOracle.forward``: the reference's algorithm, STMGCN.py:100-119, as recurrence on features) in float64 and stores
+it in ``tests/golden/bench_loss.json``.  bench.py compares the loss its timed step produces with the stored value, so a
+kernel that is fast but wrong at the BENCHMARKED size cannot print a number.
+
+    python oracle/make_bench_loss.py [workload ...]      (default: cfg3 ranks 0-7, cfg2 rank 0)
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path[:0] = [REPO, os.path.join(REPO, "st-mgcn_b200"), HERE]
+OUT = os.path.join(REPO, "tests", "golden", "bench_loss.json")
+
+
+def reference_loss(w, batch, rank, dtype=np.float64):
+    import stmgcn_oracle as O
+    from stmgcn_b200 import synth
+    from stmgcn_b200.preprocess import Adj_Preprocessor
+    from stmgcn_b200 import modules
+    pre = Adj_Preprocessor("chebyshev", w.cheb_order)
+    laps = []
+    for a in synth.make_adjacency_list(w):
+        s = pre.process_sparse(a)
+        laps.append(sp.csr_matrix((s.vals.numpy(), s.colidx.numpy(), s.rowptr.numpy()), shape=(s.n, s.n)))
+    torch.manual_seed(0)
+    model = modules.ST_MGCN(**synth.model_kwargs(w))
+    params = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    x, y = synth.make_inputs(w, seed=100 + rank, batch=batch)
+    orc = O.SparseOracle(params, laps, w.n_supports, dtype=dtype)
+    out = orc.forward(x.numpy())
+    diff = out - y.numpy().astype(dtype)
+    return float(np.mean(diff * diff))
+
+
+def main():
+    from stmgcn_b200 import synth
+    jobs = [("cfg3", 64, r) for r in range(8)] + [("cfg2", 32, 0), ("cfg1", 8, 0)]
+    if len(sys.argv) > 1:
+        jobs = [j for j in jobs if j[0] in sys.argv[1:]]
+    table = json.load(open(OUT)) if os.path.exists(OUT) else {}
+    for name, batch, rank in jobs:
+        key = f"{name}/batch{batch}/rank{rank}"
+        t0 = time.time()
+        table[key] = reference_loss(synth.WORKLOADS[name], batch, rank)
+        print(f"{key}: loss {table[key]:.9f}  ({time.time() - t0:.0f}s)", flush=True)
+        with open(OUT, "w") as fh:
+            json.dump(table, fh, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

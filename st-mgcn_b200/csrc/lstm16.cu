@@ -1,0 +1,1093 @@
+// K3b, second generation (H = 64): the shared LSTM of CG_LSTM (reference STMGCN.py:21-22, :47-50; nn.LSTM semantics)
+// on tcgen05 with bf16 hi/lo PLANES ("3xBF16", see tc16.cuh) and NO gate tape.
+//
+// Tape written by the forward (all the backward needs; it recomputes the gates from it):
+//   hp : (L, T, P, rows, 64) bf16  -- the hidden state of every layer-step as P planes (P = 2: hi | lo, fp32-grade
+//        arithmetic; P = 1: hi only, the bf16 mode).  A 128-row x 64-column piece of a plane IS a K-major, 128-byte
+//        swizzled tcgen05 operand tile once a TMA tensor load has put it into shared memory -- no splitter warps, no
+//        per-thread loads, no proxy fences on the operand path.
+//   cs : (L, T, rows_pad, 64) fp32, tile-blocked ([tile][unit/8][128 rows][8 units], see ws_off).
+// 4 + 4 bytes per (row, unit, layer-step) instead of 4 + 4 + 16 with the gate tape of the first generation
+// (lstm_tc.cu): 4.8 GB instead of 14.5 GB per graph branch at BASELINE configs[2], and configs[4] fits.
+//
+// forward kernel (one launch per layer-step, persistent, one CTA per SM):
+//   producer warp : loads the layer's weight image ONCE (resident for the whole launch: [256 gate cols][64 k] bf16 tiles,
+//                   hi and lo, per K segment = 128 KB) and streams the A planes of every tile through a ring of 16 KB
+//                   stages with TMA tensor loads (h_below hi, h_below lo, h_prev hi, h_prev lo)
+//   MMA warp      : per tile 8 (P = 1) or 24 (P = 2) tcgen05.mma kind::f16 (M 128, N 256, K 16) into one of two TMEM
+//                   accumulators: Ahi.Whi + Ahi.Wlo + Alo.Whi
+//   16 epilogue warps: TMEM -> registers -> bias (+ layer 0: x*s . W_ih in exact fp32) -> gates -> c, h -> h split into
+//                   bf16 planes -> coalesced global stores.  Nothing of the gates leaves the SM.
+#include "tc16.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+using namespace stmgcn;
+using namespace stmgcn::tc;
+
+namespace stmgcn {
+bool make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int64_t slices);
+}
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kHid = 64;
+constexpr int kGateCols = 256;
+constexpr int kMaxC = 4;
+constexpr int kWTileBytes = kGateCols * 128;          // [256 gate cols][64 k] bf16 = 32 KB
+constexpr int kATileBytes = kTile16Bytes;             // [128 rows][64 k] bf16 = 16 KB
+
+// element (row r, unit u) of a tile-blocked (rows_pad x 64) fp32 workspace
+__device__ __forceinline__ int64_t ws_off(int64_t r, int unit) {
+    return (((r >> 7) * 8 + (unit >> 3)) * kTileM + (r & 127)) * 8 + (unit & 7);
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+constexpr int kFEpiWarps = 16;
+constexpr int kFThreads = (kFEpiWarps + 2) * 32;       // + MMA warp + producer warp
+constexpr int kFStages = 5;
+
+struct F16Tail {
+    float bias[kGateCols];
+    float wih[kMaxC * kGateCols];
+    uint64_t full[kFStages];
+    uint64_t empty[kFStages];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint64_t w_full;
+    uint32_t tmem_base;
+};
+constexpr size_t kFSmem = 1024 + 4 * (size_t)kWTileBytes + (size_t)kFStages * kATileBytes + sizeof(F16Tail);
+static_assert(kFSmem <= 232448, "lstm16 forward kernel exceeds the 227 KB shared-memory limit");
+
+struct Fwd16Params {
+    alignas(64) CUtensorMap amap[2];   // per K segment: (64, rows, slices) bf16 view of a plane tensor, box 64 x 128 x 1, 128B swizzle
+    int aslice[2];                     // slice of the segment's hi plane (lo plane = +1)
+    int nseg;                          // K segments present: layer 0: h_prev; layers > 0: h_below, h_prev (absent at t = 0 without h0)
+    const uint8_t* wimg;               // tiles [(seg*2 + plane)] of 32 KB
+    const float* bias;                 // (256) gate-interleaved b_ih + b_hh
+    const float* wih;                  // layer 0: (C, 256) gate-interleaved W_ih^T; else nullptr
+    const float* xo;                   // (rows, T, C)
+    const float* sg;                   // (B, T)
+    int c_in, t, t_len;
+    int64_t b_inner;
+    const float* c_prev;               // tile-blocked or nullptr (zeros)
+    float* c_out;                      // tile-blocked
+    uint16_t* h_hi;                    // (rows, 64) bf16 plane
+    uint16_t* h_lo;                    // (rows, 64) bf16 plane (PLANES = 2)
+    float* h_f32;                      // (rows, 64) fp32 copy of h or nullptr
+    int64_t rows;
+    int n_tiles;
+};
+
+template <int PLANES>
+__global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_constant__ Fwd16Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* wsm = smem;                                           // resident weight tiles
+    uint8_t* stages = smem + 4 * (size_t)kWTileBytes;
+    F16Tail* tail = (F16Tail*)(stages + (size_t)kFStages * kATileBytes);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    constexpr int kMmaWarp = kFEpiWarps;
+    constexpr int kProdWarp = kFEpiWarps + 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < kFStages; ++s) {
+            mbar_init(&tail->full[s], 1);
+            mbar_init(&tail->empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tail->tmem_full[a], 1);
+            mbar_init(&tail->tmem_empty[a], kFEpiWarps * 32);
+        }
+        mbar_init(&tail->w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, 512);
+    for (int i = tid; i < kGateCols; i += kFThreads) tail->bias[i] = p.bias[i];
+    if (p.wih != nullptr)
+        for (int i = tid; i < p.c_in * kGateCols; i += kFThreads) tail->wih[i] = p.wih[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == kProdWarp) {
+        // ===================== producer: resident weights once, then the A planes of every tile =====================
+        if (lane == 0 && p.nseg > 0) {
+            mbar_arrive_expect_tx(&tail->w_full, (uint32_t)(p.nseg * PLANES * kWTileBytes));
+            for (int s = 0; s < p.nseg; ++s)
+                for (int pl = 0; pl < PLANES; ++pl)
+                    bulk_g2s(wsm + (size_t)(s * 2 + pl) * kWTileBytes, p.wimg + (size_t)(s * 2 + pl) * kWTileBytes, kWTileBytes,
+                             &tail->w_full);
+            uint32_t it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int tile = blockIdx.x + i * gridDim.x;
+                for (int s = 0; s < p.nseg; ++s)
+                    for (int pl = 0; pl < PLANES; ++pl, ++it) {
+                        const int stg = it % kFStages;
+                        const uint32_t ph = (it / kFStages) & 1;
+                        mbar_wait_raw(&tail->empty[stg], ph ^ 1);
+                        mbar_arrive_expect_tx(&tail->full[stg], kATileBytes);
+                        tma_load_3d(stages + (size_t)stg * kATileBytes, &p.amap[s], 0, tile * kTileM, p.aslice[s] + pl,
+                                    &tail->full[stg]);
+                    }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ===================== MMA issuer =====================
+        if (p.nseg > 0) {
+            constexpr uint32_t idesc = idesc_bf16(kTileM, kGateCols);
+            mbar_wait_raw(&tail->w_full, 0);
+            tc_fence_after();
+            uint32_t it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int a = i & 1;
+                const uint32_t aph = (uint32_t)(i >> 1) & 1;
+                mbar_wait_raw(&tail->tmem_empty[a], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)a * kGateCols;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const uint64_t w_hi = desc16_k(smem_u32(wsm + (size_t)(s * 2) * kWTileBytes));
+                    const uint64_t w_lo = desc16_k(smem_u32(wsm + (size_t)(s * 2 + 1) * kWTileBytes));
+                    {   // hi plane of the segment: against W hi (and W lo)
+                        const int stg = it % kFStages;
+                        const uint32_t ph = (it / kFStages) & 1;
+                        mbar_wait_raw(&tail->full[stg], ph);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint64_t a_d = desc16_k(smem_u32(stages + (size_t)stg * kATileBytes));
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                mma_bf16(d_tmem, a_d + (uint64_t)(2 * kk), w_hi + (uint64_t)(2 * kk), idesc, (s > 0 || kk > 0) ? 1u : 0u);
+                            if (PLANES == 2) {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    mma_bf16(d_tmem, a_d + (uint64_t)(2 * kk), w_lo + (uint64_t)(2 * kk), idesc, 1u);
+                            }
+                            mma_commit(&tail->empty[stg]);
+                        }
+                        __syncwarp();
+                        ++it;
+                    }
+                    if (PLANES == 2) {   // lo plane of the segment: against W hi
+                        const int stg = it % kFStages;
+                        const uint32_t ph = (it / kFStages) & 1;
+                        mbar_wait_raw(&tail->full[stg], ph);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint64_t a_d = desc16_k(smem_u32(stages + (size_t)stg * kATileBytes));
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                mma_bf16(d_tmem, a_d + (uint64_t)(2 * kk), w_hi + (uint64_t)(2 * kk), idesc, 1u);
+                            mma_commit(&tail->empty[stg]);
+                        }
+                        __syncwarp();
+                        ++it;
+                    }
+                }
+                if (lane == 0) mma_commit(&tail->tmem_full[a]);
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== epilogue: LSTM cell =====================
+        // TMEM lane quadrant q = warp & 3 (rows 32q .. 32q+31 of the tile), column quarter part = warp >> 2
+        // (gate columns 64*part .. +63 = units 16*part .. +15), four pieces of 16 columns = 4 units each
+        const int q = warp & 3, part = warp >> 2;
+        const bool l0 = p.wih != nullptr;
+        float cpv[16];
+        float xs[kMaxC];
+        auto prefetch = [&](int tile_n) {       // c_{t-1} (and layer 0: x*s) of this thread's row, one tile ahead
+            const int64_t rn = (int64_t)tile_n * kTileM + q * 32 + lane;
+            const bool ok = tile_n < p.n_tiles && rn < p.rows;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok && p.c_prev != nullptr) v = *reinterpret_cast<const float4*>(p.c_prev + ws_off(rn, part * 16 + 4 * j));
+                cpv[4 * j] = v.x; cpv[4 * j + 1] = v.y; cpv[4 * j + 2] = v.z; cpv[4 * j + 3] = v.w;
+            }
+            if (l0) {
+                float sv = 0.f;
+                if (ok) sv = p.sg[(rn % p.b_inner) * p.t_len + p.t];
+#pragma unroll
+                for (int c = 0; c < kMaxC; ++c) xs[c] = (ok && c < p.c_in) ? p.xo[(rn * p.t_len + p.t) * p.c_in + c] * sv : 0.f;
+            }
+        };
+        prefetch((int)blockIdx.x);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int a = i & 1;
+            const uint32_t aph = (uint32_t)(i >> 1) & 1;
+            const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
+            const bool valid = r < p.rows;
+            if (p.nseg > 0) {
+                mbar_wait_raw(&tail->tmem_full[a], aph);
+                tc_fence_after();
+            }
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * kGateCols + (uint32_t)part * 64;
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) {
+                uint32_t v[16];
+                if (p.nseg > 0) {
+                    tmem_ld16(t_row + pc * 16, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0u;
+                }
+                const int unit0 = part * 16 + pc * 4;
+                float hn[4], cn[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int col = 4 * (unit0 + u);
+                    const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[col]);
+                    float pi = __uint_as_float(v[4 * u + 0]) + bv.x;
+                    float pf = __uint_as_float(v[4 * u + 1]) + bv.y;
+                    float pg = __uint_as_float(v[4 * u + 2]) + bv.z;
+                    float po = __uint_as_float(v[4 * u + 3]) + bv.w;
+                    if (l0) {
+#pragma unroll
+                        for (int c = 0; c < kMaxC; ++c)
+                            if (c < p.c_in) {
+                                const float4 wv = *reinterpret_cast<const float4*>(&tail->wih[c * kGateCols + col]);
+                                pi = fmaf(xs[c], wv.x, pi); pf = fmaf(xs[c], wv.y, pf);
+                                pg = fmaf(xs[c], wv.z, pg); po = fmaf(xs[c], wv.w, po);
+                            }
+                    }
+                    const float gi = sigmoidf_(pi), gf = sigmoidf_(pf), gg = tanhf_(pg), go = sigmoidf_(po);
+                    cn[u] = fmaf(gf, cpv[4 * pc + u], gi * gg);
+                    hn[u] = go * tanhf_(cn[u]);
+                }
+                if (PLANES == 2) {
+                    split_bf16x2(hn[0], hn[1], hi[2 * pc], lo[2 * pc]);
+                    split_bf16x2(hn[2], hn[3], hi[2 * pc + 1], lo[2 * pc + 1]);
+                } else {
+                    hi[2 * pc] = pack_bf16x2(hn[0], hn[1]);
+                    hi[2 * pc + 1] = pack_bf16x2(hn[2], hn[3]);
+                }
+                if (valid) {
+                    *reinterpret_cast<float4*>(p.c_out + ws_off(r, unit0)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    if (p.h_f32 != nullptr)
+                        *reinterpret_cast<float4*>(p.h_f32 + r * kHid + unit0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                }
+            }
+            if (p.nseg > 0) {          // all TMEM reads of this accumulator are done
+                tc_fence_before();
+                mbar_arrive(&tail->tmem_empty[a]);
+            }
+            if (valid) {
+                uint4* dh = reinterpret_cast<uint4*>(p.h_hi + r * kHid + part * 16);
+                dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                if (PLANES == 2) {
+                    uint4* dl = reinterpret_cast<uint4*>(p.h_lo + r * kHid + part * 16);
+                    dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
+            }
+            prefetch(tile + (int)gridDim.x);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- weight image packer: nn.LSTM parameters of one layer -> resident operand tiles + interleaved bias / W_ih^T ----
+// tile (seg, plane): [256 rows n = 4*unit + gate][64 k] bf16, 128-byte swizzle; seg 0 = W_ih (layers > 0) or W_hh (layer 0),
+// seg 1 = W_hh (layers > 0).  Native row of gate-interleaved column n: (n & 3) * 64 + (n >> 2)  (gate order i, f, g, o).
+__global__ void lstm16_pack_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                   const float* __restrict__ b_ih, const float* __restrict__ b_hh, int layer, int c_in,
+                                   uint8_t* __restrict__ wimg, float* __restrict__ bias, float* __restrict__ wih_t) {
+    const int nseg = layer == 0 ? 1 : 2;
+    const int total = nseg * kGateCols * kHid;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int s = e / (kGateCols * kHid), n = (e / kHid) % kGateCols, k = e % kHid;
+        const int nat = (n & 3) * kHid + (n >> 2);
+        const float* src = (layer > 0 && s == 0) ? w_ih : w_hh;
+        const float v = src[(int64_t)nat * kHid + k];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+        const uint32_t off = sw128_off16((uint32_t)n, (uint32_t)k);
+        *reinterpret_cast<__nv_bfloat16*>(wimg + (size_t)(s * 2) * kWTileBytes + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(wimg + (size_t)(s * 2 + 1) * kWTileBytes + off) = l;
+    }
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < kGateCols; n += gridDim.x * blockDim.x) {
+        const int nat = (n & 3) * kHid + (n >> 2);
+        bias[n] = b_ih[nat] + b_hh[nat];
+        if (layer == 0 && wih_t != nullptr)
+            for (int c = 0; c < c_in; ++c) wih_t[c * kGateCols + n] = w_ih[(int64_t)nat * c_in + c];
+    }
+}
+
+
+// =====================================================================================================
+// backward: gate recompute + BPTT pointwise + data gradient + weight gradient in ONE kernel per layer-step
+// =====================================================================================================
+// Per 128-row tile, the 256 gate columns are processed as four chunks of 64 (16 units x i,f,g,o):
+//   R_c : recompute the chunk's pre-activations  G_c[128 x 64] = [h_below | h_prev] . Wp[:, chunk]     (TMEM, 2 buffers)
+//   P_c : 16 compute warps: TMEM -> gates -> c_t, tanh(c_t) -> BPTT pointwise -> dA_c (fp32) -> bf16 hi/lo planes in a
+//         128-byte-swizzled shared-memory tile; dc in place; bias gradient by a 16-shuffle halving reduction
+//   W_c : weight gradient   dWp[:, chunk] += [h_below | h_prev]^T . dA_c   -- BOTH operands are the MN-major view of tiles
+//         that are already in shared memory (the A planes, dA_c); one 256-column TMEM accumulator lives for the launch
+//   D_c : data gradient     [dx_below | dh_prev] += dA_c . Wp[:, chunk]^T  -- B is the MN-major view of the weight chunk
+//         R_c used; 128-column TMEM accumulator, drained by the compute warps at the start of the next tile
+// dA never leaves the SM; the gates are never stored.  HBM traffic per tile: A planes 64 KB + c_prev, dh_in, dh_rec, dc
+// (4 x 32 KB) in, dc, dh_rec, dx_below (3 x 32 KB) out = 288 KB (the first-generation pair of kernels moved 640 KB).
+// Weight chunks stream from L2 through a 3-stage ring (a chunk is needed early by R_c and two chunk-times later by D_c).
+// Partial weight gradients: every CTA adds its TMEM accumulator into its OWN slice of a scratch buffer with plain coalesced
+// read-modify-writes (no atomics; the slice layout is the accumulator's register layout); stmgcn_lstm16_wgrad_reduce sums
+// the slices once per layer and writes nn.LSTM-native gradients.
+constexpr int kBCompWarps = 16;
+constexpr int kBThreads = (kBCompWarps + 2) * 32;       // + MMA warp + producer warp
+constexpr int kBWStages = 3;
+constexpr int kBWChunkTile = 64 * 128;                  // [64 gate cols][64 k] bf16 = 8 KB
+constexpr int kBWStageBytes = 4 * kBWChunkTile;         // (seg0 hi | seg0 lo | seg1 hi | seg1 lo) = 32 KB
+constexpr int kBSgMax = 1024;
+
+struct B16Tail {
+    float bias[kGateCols];
+    float wih[kMaxC * kGateCols];
+    float s_db[kGateCols];
+    float s_ds[kBSgMax];
+    uint64_t a_full, a_empty;
+    uint64_t w_full[kBWStages], w_empty[kBWStages];
+    uint64_t r_full[2], r_empty[2];
+    uint64_t d_full, d_empty;
+    uint64_t g_full, g_empty;
+    uint64_t done;
+    uint32_t tmem_base;
+};
+constexpr size_t kBSmem = 1024 + 4 * (size_t)kATileBytes + (size_t)kBWStages * kBWStageBytes + 2 * (size_t)kATileBytes + sizeof(B16Tail);
+static_assert(kBSmem <= 232448, "lstm16 backward kernel exceeds the 227 KB shared-memory limit");
+
+struct Bwd16Params {
+    alignas(64) CUtensorMap amap[2];
+    int aslice[2];
+    int nseg;                  // K segments of the gate GEMM present (0, 1, 2)
+    int layer0;                // 1: layer 0 (segment = h_prev only; tiles 2,3 of the A region hold the [x*s] auxiliary operand)
+    const uint8_t* wimg;
+    const float* bias;
+    const float* wih;          // layer 0: (C,256) gate-interleaved
+    const float* xo;           // (rows, T, C)
+    const float* sg;           // (B, T)
+    float* d_s;                // (B, T) +=   (layer 0)
+    int c_in, t, t_len;
+    int64_t b_inner;
+    const float* c_prev;       // blocked or nullptr
+    const float* dh_in;        // blocked or nullptr: gradient from the layer above (or d_top)
+    float* dh_rec;             // blocked, in (unless first) / out
+    float* dc;                 // blocked, in (unless first) / out
+    float* dx_out;             // blocked or nullptr (layer 0)
+    int first;                 // t == T-1: incoming dh_rec / dc are zero and not read
+    int store_dh;              // write dh_prev (t > 0 or an initial state exists)
+    float* dbp;                // (256) +=  gate-interleaved bias gradient
+    float* dw_slice;           // this launch's scratch: gridDim.x slices of 128*256 floats (accumulator register layout)
+    int dw_first;              // 1: first launch of this layer: slices are written, not accumulated
+    int flush_lo, flush_hi;    // accumulator rows [0,64) / [64,128) carry a valid gradient in this launch
+    int64_t rows;
+    int n_tiles;
+};
+
+template <int PLANES>
+__global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_constant__ Bwd16Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_sm = smem;                                          // tiles 0..3: seg0 hi | seg0 lo | seg1 (aux) hi | seg1 (aux) lo
+    uint8_t* w_sm = a_sm + 4 * (size_t)kATileBytes;                // weight chunk ring
+    uint8_t* da_sm = w_sm + (size_t)kBWStages * kBWStageBytes;     // dA chunk: hi tile | lo tile
+    B16Tail* tail = (B16Tail*)(da_sm + 2 * (size_t)kATileBytes);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    constexpr int kMmaWarp = kBCompWarps;
+    constexpr int kProdWarp = kBCompWarps + 1;
+    constexpr int kCompThreads = kBCompWarps * 32;
+    constexpr uint32_t kWgCol = 0, kDgCol = 256, kRcCol = 384;     // TMEM columns: weight grad | data grad | recompute x2
+
+    if (tid == 0) {
+        mbar_init(&tail->a_full, 1);
+        mbar_init(&tail->a_empty, 1);
+        for (int s = 0; s < kBWStages; ++s) {
+            mbar_init(&tail->w_full[s], 1);
+            mbar_init(&tail->w_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tail->r_full[b], 1);
+            mbar_init(&tail->r_empty[b], kCompThreads);
+        }
+        mbar_init(&tail->d_full, kCompThreads);
+        mbar_init(&tail->d_empty, 1);
+        mbar_init(&tail->g_full, 1);
+        mbar_init(&tail->g_empty, kCompThreads);
+        mbar_init(&tail->done, 1);
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, 512);
+    for (int i = tid; i < kGateCols; i += kBThreads) {
+        tail->bias[i] = p.bias[i];
+        tail->s_db[i] = 0.f;
+    }
+    if (p.layer0) {
+        for (int i = tid; i < p.c_in * kGateCols; i += kBThreads) tail->wih[i] = p.wih[i];
+        for (int i = tid; i < kBSgMax; i += kBThreads) tail->s_ds[i] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+    const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool have_aux = p.layer0 != 0;
+    // operand tiles of the weight-gradient GEMM (MN-major view): atom 0 and atom 1 along M = kd
+    // layers > 0: atom 0 = h_below, atom 1 = h_prev (absent: duplicate of atom 0, rows 64.. are not flushed)
+    // layer 0   : atom 0 = h_prev (absent at t = 0: duplicate of the auxiliary tile), atom 1 = auxiliary [x*s] tile
+    const uint32_t wg_a0 = (p.layer0 && p.nseg == 0) ? 2u : 0u;
+    const uint32_t wg_lbo = (p.layer0 ? (p.nseg == 0 ? 0u : 2u) : (p.nseg == 2 ? 2u : 0u)) * kATileBytes;
+
+    if (warp == kProdWarp) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            uint32_t wc = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int tile = blockIdx.x + i * gridDim.x;
+                if (p.nseg > 0) {
+                    if (i > 0) mbar_wait_raw(&tail->a_empty, (uint32_t)(i - 1) & 1);
+                    mbar_arrive_expect_tx(&tail->a_full, (uint32_t)(p.nseg * PLANES * kATileBytes));
+                    for (int s = 0; s < p.nseg; ++s)
+                        for (int pl = 0; pl < PLANES; ++pl)
+                            tma_load_3d(a_sm + (size_t)(s * 2 + pl) * kATileBytes, &p.amap[s], 0, tile * kTileM, p.aslice[s] + pl,
+                                        &tail->a_full);
+                    for (int c = 0; c < 4; ++c, ++wc) {
+                        const int stg = wc % kBWStages;
+                        const uint32_t ph = (wc / kBWStages) & 1;
+                        mbar_wait_raw(&tail->w_empty[stg], ph ^ 1);
+                        mbar_arrive_expect_tx(&tail->w_full[stg], (uint32_t)(p.nseg * PLANES * kBWChunkTile));
+                        for (int s = 0; s < p.nseg; ++s)
+                            for (int pl = 0; pl < PLANES; ++pl)
+                                bulk_g2s(w_sm + (size_t)stg * kBWStageBytes + (size_t)(s * 2 + pl) * kBWChunkTile,
+                                         p.wimg + (size_t)(s * 2 + pl) * kWTileBytes + (size_t)c * kBWChunkTile, kBWChunkTile,
+                                         &tail->w_full[stg]);
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_rc = idesc_bf16(kTileM, 64);              // recompute: A K-major, B K-major, N = 64
+        constexpr uint32_t idesc_wg = idesc_bf16(kTileM, 64, 1, 1);        // weight gradient: both MN-major, M = kd (128), N = 64
+        const uint32_t idesc_dg = idesc_bf16(kTileM, 64 * (p.nseg > 0 ? p.nseg : 1), 0, 1);   // data gradient: B MN-major, N = 64 * nseg
+        const uint32_t a_u = smem_u32(a_sm), w_u = smem_u32(w_sm), da_u = smem_u32(da_sm);
+        uint32_t wc_r = 0;          // weight-chunk counter of the recompute front
+        uint32_t rc = 0;            // recompute-buffer counter
+        auto issue_R = [&](int c) {
+            (void)c;
+            const int stg = wc_r % kBWStages;
+            const uint32_t ph = (wc_r / kBWStages) & 1;
+            const int b = rc & 1;
+            const uint32_t bph = (rc >> 1) & 1;
+            mbar_wait_raw(&tail->w_full[stg], ph);
+            mbar_wait_raw(&tail->r_empty[b], bph ^ 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t d = tmem_base + kRcCol + (uint32_t)b * 64;
+                const uint32_t ws = w_u + (uint32_t)stg * kBWStageBytes;
+                bool first = true;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const uint64_t a_hi = desc16_k(a_u + (uint32_t)(s * 2) * kATileBytes);
+                    const uint64_t a_lo = desc16_k(a_u + (uint32_t)(s * 2 + 1) * kATileBytes);
+                    const uint64_t b_hi = desc16_k(ws + (uint32_t)(s * 2) * kBWChunkTile);
+                    const uint64_t b_lo = desc16_k(ws + (uint32_t)(s * 2 + 1) * kBWChunkTile);
+#pragma unroll
+                    for (int pass = 0; pass < (PLANES == 2 ? 3 : 1); ++pass) {
+                        const uint64_t da = (pass == 1) ? a_lo : a_hi;
+                        const uint64_t db = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            mma_bf16(d, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc_rc, first ? 0u : 1u);
+                            first = false;
+                        }
+                    }
+                }
+                mma_commit(&tail->r_full[b]);
+            }
+            __syncwarp();
+            ++wc_r;
+            ++rc;
+        };
+        uint32_t wc_d = 0;          // weight-chunk counter of the data-gradient front
+        uint32_t dcount = 0;        // dA chunks consumed
+        for (int i = 0; i < my_tiles; ++i) {
+            if (p.nseg > 0) {
+                mbar_wait_raw(&tail->a_full, (uint32_t)i & 1);
+                tc_fence_after();
+                issue_R(0);
+                issue_R(1);
+            }
+            for (int c = 0; c < 4; ++c, ++dcount) {
+                mbar_wait_raw(&tail->d_full, dcount & 1);
+                if (c == 0 && p.nseg > 0 && i > 0) mbar_wait_raw(&tail->g_empty, (uint32_t)(i - 1) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    // ---- weight gradient: dWp[:, chunk c] += A'^T . dA_c   (M = kd 128, N = 64, K = 128 rows) ----
+                    const uint32_t d_wg = tmem_base + kWgCol + (uint32_t)c * 64;
+#pragma unroll
+                    for (int pass = 0; pass < (PLANES == 2 ? 3 : 1); ++pass) {
+                        const uint32_t a_t = a_u + (wg_a0 + (pass == 1 ? 1u : 0u)) * kATileBytes;
+                        const uint32_t b_t = da_u + (pass == 2 ? (uint32_t)kATileBytes : 0u);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_bf16(d_wg, desc16_mn(a_t + ks * 2048, wg_lbo), desc16_mn(b_t + ks * 2048, kATileBytes), idesc_wg,
+                                     (i > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    if (c == 3 && p.nseg > 0) mma_commit(&tail->a_empty);          // A planes may be refilled
+                    // ---- data gradient: [dx_below | dh_prev] += dA_c . Wp[:, chunk c]^T   (N = 64 * nseg, K = 64) ----
+                    if (p.nseg > 0) {
+                        const int stg = wc_d % kBWStages;
+                        const uint32_t ws = w_u + (uint32_t)stg * kBWStageBytes;
+                        const uint32_t d_dg = tmem_base + kDgCol;
+#pragma unroll
+                        for (int pass = 0; pass < (PLANES == 2 ? 3 : 1); ++pass) {
+                            const uint64_t da = desc16_k(da_u + (pass == 1 ? (uint32_t)kATileBytes : 0u));
+                            const uint32_t b_t = ws + (pass == 2 ? (uint32_t)kBWChunkTile : 0u);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                mma_bf16(d_dg, da + (uint64_t)(2 * kk), desc16_mn(b_t + kk * 2048, 2 * kBWChunkTile), idesc_dg,
+                                         (c > 0 || pass > 0 || kk > 0) ? 1u : 0u);
+                        }
+                        mma_commit(&tail->w_empty[stg]);
+                    }
+                    mma_commit(&tail->d_empty);
+                    if (c == 3 && p.nseg > 0) mma_commit(&tail->g_full);
+                }
+                __syncwarp();
+                if (p.nseg > 0) {
+                    ++wc_d;
+                    if (c + 2 < 4) issue_R(c + 2);
+                }
+            }
+        }
+        if (lane == 0) mma_commit(&tail->done);
+        __syncwarp();
+    } else {
+        // ===================== compute warps =====================
+        // TMEM lane quadrant q = warp & 3 (row 32q + lane of the tile), part = warp >> 2: units 4*part .. +3 of every chunk
+        const int q = warp & 3, part = warp >> 2;
+        const int ctid = tid;
+        (void)ctid;
+        float xs[kMaxC], xraw[kMaxC], dxs[kMaxC];
+        uint32_t dcount = 0, rcount = 0;
+        // raw inputs of one chunk: c_prev, dh_in, dh_rec, dc of this thread's 4 units
+        struct Raw { float4 cp, dhi, dhr, dcv; };
+        auto load_raw = [&](int tile, int c, Raw& rw) {
+            const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            rw.cp = rw.dhi = rw.dhr = rw.dcv = z;
+            if (tile < p.n_tiles && r < p.rows) {
+                const int64_t o = ws_off(r, 16 * c + 4 * part);
+                if (p.c_prev) rw.cp = *reinterpret_cast<const float4*>(p.c_prev + o);
+                if (p.dh_in) rw.dhi = *reinterpret_cast<const float4*>(p.dh_in + o);
+                if (!p.first) {
+                    rw.dhr = *reinterpret_cast<const float4*>(p.dh_rec + o);
+                    rw.dcv = *reinterpret_cast<const float4*>(p.dc + o);
+                }
+            }
+        };
+        auto drain = [&](int i_prev) {          // [dx_below | dh_prev] of tile i_prev: TMEM -> tile-blocked workspaces
+            const int tile = blockIdx.x + i_prev * gridDim.x;
+            const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
+            mbar_wait_raw(&tail->g_full, (uint32_t)i_prev & 1);
+            tc_fence_after();
+            const int ncols = 64 * p.nseg;
+            if (part * 32 < ncols) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kDgCol + (uint32_t)part * 32, v);
+                tmem_ld_wait();
+                const int col = part * 32;
+                // layers > 0: columns [0,64) = dx_below, [64,128) = dh_prev; layer 0: [0,64) = dh_prev
+                const bool is_dx = !p.layer0 && col < 64;
+                float* base = is_dx ? p.dx_out : p.dh_rec;
+                const int unit0 = col & 63;
+                if (r < p.rows && base != nullptr && (is_dx || p.store_dh)) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(base + ws_off(r, unit0 + 4 * j)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tail->g_empty);
+        };
+        Raw cur, nxt;
+        load_raw((int)blockIdx.x, 0, nxt);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
+            const bool valid = r < p.rows;
+            if (p.layer0) {
+                float sv = 0.f;
+                if (valid) sv = p.sg[(r % p.b_inner) * p.t_len + p.t];
+#pragma unroll
+                for (int c = 0; c < kMaxC; ++c) {
+                    xraw[c] = (valid && c < p.c_in) ? p.xo[(r * p.t_len + p.t) * p.c_in + c] : 0.f;
+                    xs[c] = xraw[c] * sv;
+                    dxs[c] = 0.f;
+                }
+            }
+            if (i > 0 && p.nseg > 0) drain(i - 1);
+            if (have_aux && part == 0) {
+                // auxiliary weight-gradient operand: tile 2 (hi) / tile 3 (lo), row = this thread's row, columns 0..C-1 = x*s
+                if (i > 0 && p.nseg > 0) mbar_wait_raw(&tail->a_empty, (uint32_t)(i - 1) & 1);
+                else if (i > 0) mbar_wait_raw(&tail->d_empty, (dcount - 1) & 1);      // no A planes: the last W_3 read the tile
+                uint32_t hi[2], lo[2];
+                split_bf16x2(xs[0], xs[1], hi[0], lo[0]);
+                split_bf16x2(xs[2], xs[3], hi[1], lo[1]);
+                const uint32_t row = (uint32_t)(q * 32 + lane);
+                const uint32_t off = row * 128u + ((0u ^ (row & 7u)) << 4);
+                *reinterpret_cast<uint4*>(a_sm + 2 * (size_t)kATileBytes + off) = make_uint4(hi[0], hi[1], 0u, 0u);
+                *reinterpret_cast<uint4*>(a_sm + 3 * (size_t)kATileBytes + off) = make_uint4(lo[0], lo[1], 0u, 0u);
+            }
+            for (int c = 0; c < 4; ++c, ++dcount) {
+                cur = nxt;
+                if (c < 3) load_raw(tile, c + 1, nxt);
+                else load_raw(tile + (int)gridDim.x, 0, nxt);
+                uint32_t v[16];
+                if (p.nseg > 0) {
+                    const int b = rcount & 1;
+                    mbar_wait_raw(&tail->r_full[b], (rcount >> 1) & 1);
+                    tc_fence_after();
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kRcCol + (uint32_t)b * 64 + (uint32_t)part * 16, v);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(&tail->r_empty[b]);
+                    ++rcount;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0u;
+                }
+                const int unit0 = 16 * c + 4 * part;
+                const float cp[4] = {cur.cp.x, cur.cp.y, cur.cp.z, cur.cp.w};
+                const float dhi[4] = {cur.dhi.x, cur.dhi.y, cur.dhi.z, cur.dhi.w};
+                const float dhr[4] = {cur.dhr.x, cur.dhr.y, cur.dhr.z, cur.dhr.w};
+                const float dci[4] = {cur.dcv.x, cur.dcv.y, cur.dcv.z, cur.dcv.w};
+                float da[16], dcn[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int col = 4 * (unit0 + u);
+                    const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[col]);
+                    float pi = __uint_as_float(v[4 * u + 0]) + bv.x;
+                    float pf = __uint_as_float(v[4 * u + 1]) + bv.y;
+                    float pg = __uint_as_float(v[4 * u + 2]) + bv.z;
+                    float po = __uint_as_float(v[4 * u + 3]) + bv.w;
+                    if (p.layer0) {
+#pragma unroll
+                        for (int cc = 0; cc < kMaxC; ++cc)
+                            if (cc < p.c_in) {
+                                const float4 wv = *reinterpret_cast<const float4*>(&tail->wih[cc * kGateCols + col]);
+                                pi = fmaf(xs[cc], wv.x, pi); pf = fmaf(xs[cc], wv.y, pf);
+                                pg = fmaf(xs[cc], wv.z, pg); po = fmaf(xs[cc], wv.w, po);
+                            }
+                    }
+                    const float gi = sigmoidf_(pi), gf = sigmoidf_(pf), gg = tanhf_(pg), go = sigmoidf_(po);
+                    const float ct = fmaf(gf, cp[u], gi * gg);
+                    const float tc_ = tanhf_(ct);
+                    const float dh = valid ? (dhr[u] + dhi[u]) : 0.f;
+                    const float dcv = valid ? fmaf(dh * go, 1.f - tc_ * tc_, dci[u]) : 0.f;
+                    da[4 * u + 0] = dcv * gg * gi * (1.f - gi);
+                    da[4 * u + 1] = dcv * cp[u] * gf * (1.f - gf);
+                    da[4 * u + 2] = dcv * gi * (1.f - gg * gg);
+                    da[4 * u + 3] = dh * tc_ * go * (1.f - go);
+                    dcn[u] = dcv * gf;
+                    if (p.layer0) {
+#pragma unroll
+                        for (int cc = 0; cc < kMaxC; ++cc)
+                            if (cc < p.c_in) {
+                                const float4 wv = *reinterpret_cast<const float4*>(&tail->wih[cc * kGateCols + col]);
+                                dxs[cc] += da[4 * u] * wv.x + da[4 * u + 1] * wv.y + da[4 * u + 2] * wv.z + da[4 * u + 3] * wv.w;
+                            }
+                    }
+                }
+                // dA chunk -> bf16 planes, 128-byte-swizzled tile: row = this thread's row, columns 16*part .. +15
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (PLANES == 2) split_bf16x2(da[2 * j], da[2 * j + 1], hi[j], lo[j]);
+                    else hi[j] = pack_bf16x2(da[2 * j], da[2 * j + 1]);
+                }
+                if (dcount > 0) mbar_wait_raw(&tail->d_empty, (dcount - 1) & 1);     // W_{c-1}, D_{c-1} have read the dA tile
+                {
+                    const uint32_t row = (uint32_t)(q * 32 + lane);
+                    const uint32_t o0 = row * 128u + ((((uint32_t)(2 * part)) ^ (row & 7u)) << 4);
+                    const uint32_t o1 = row * 128u + ((((uint32_t)(2 * part + 1)) ^ (row & 7u)) << 4);
+                    *reinterpret_cast<uint4*>(da_sm + o0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(da_sm + o1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    if (PLANES == 2) {
+                        *reinterpret_cast<uint4*>(da_sm + kATileBytes + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(da_sm + kATileBytes + o1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&tail->d_full);
+                if (valid) *reinterpret_cast<float4*>(p.dc + ws_off(r, unit0)) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+                // bias gradient: column sums over the warp's 32 rows by a halving butterfly (16 shuffles), then one
+                // shared-memory atomic per column from the even lanes
+                {
+                    float s8[8], s4[4], s2[2], s1;
+                    const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0, u2 = (lane & 2) != 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float send = u16 ? da[j] : da[j + 8];
+                        const float keep = u16 ? da[j + 8] : da[j];
+                        s8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float send = u8 ? s8[j] : s8[j + 4];
+                        const float keep = u8 ? s8[j + 4] : s8[j];
+                        s4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const float send = u4 ? s4[j] : s4[j + 2];
+                        const float keep = u4 ? s4[j + 2] : s4[j];
+                        s2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    {
+                        const float send = u2 ? s2[0] : s2[1];
+                        const float keep = u2 ? s2[1] : s2[0];
+                        s1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+                    if ((lane & 1) == 0) {
+                        const int j = (u16 ? 8 : 0) + (u8 ? 4 : 0) + (u4 ? 2 : 0) + (u2 ? 1 : 0);
+                        atomicAdd(&tail->s_db[4 * unit0 + j], s1);
+                    }
+                }
+            }
+            if (p.layer0 && valid) {
+                // gate adjoint: d s[b, t] += sum_c dxmod[r, c] * xo[r, t, c]   (STMGCN.py:44)
+                float contrib = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < kMaxC; ++cc) contrib += dxs[cc] * xraw[cc];
+                const int64_t b = r % p.b_inner;
+                if (p.b_inner <= kBSgMax) atomicAdd(&tail->s_ds[b], contrib);
+                else atomicAdd(&p.d_s[b * p.t_len + p.t], contrib);
+            }
+        }
+        if (my_tiles > 0 && p.nseg > 0) drain(my_tiles - 1);
+        // ---- weight-gradient accumulator -> this CTA's scratch slice (register layout: [part][piece][vec][row m][4]) ----
+        if (my_tiles > 0) {
+            mbar_wait_raw(&tail->done, 0);
+            tc_fence_after();
+            float* slice = p.dw_slice + (size_t)blockIdx.x * (kTileM * kGateCols);
+            const int m = q * 32 + lane;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kWgCol + (uint32_t)part * 64 + (uint32_t)j * 16, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float4* dst = reinterpret_cast<float4*>(slice + ((size_t)((part * 4 + j) * 4 + e) * kTileM + m) * 4);
+                    float4 acc = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                                             __uint_as_float(v[4 * e + 3]));
+                    const bool live = (q < 2) ? (p.flush_lo != 0) : (p.flush_hi != 0);      // rows m < 64 / m >= 64
+                    if (live) {
+                        if (!p.dw_first) {
+                            const float4 old = *dst;
+                            acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+                        }
+                        *dst = acc;
+                    } else if (p.dw_first) {
+                        *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+    for (int i = tid; i < kGateCols; i += kBThreads) atomicAdd(&p.dbp[i], tail->s_db[i]);
+    if (p.layer0 && p.b_inner <= kBSgMax)
+        for (int i = tid; i < (int)p.b_inner; i += kBThreads) atomicAdd(&p.d_s[(int64_t)i * p.t_len + p.t], tail->s_ds[i]);
+}
+
+// Sum the per-CTA weight-gradient slices of one layer and write nn.LSTM-native gradients:
+//   d_w_ih (256, in), d_w_hh (256, 64), d_b_ih = d_b_hh (256); native row of gate-interleaved column n: (n & 3) * 64 + (n >> 2).
+// Accumulator row m = kd index: layers > 0: m < 64 -> W_ih[:, m], m >= 64 -> W_hh[:, m - 64]; layer 0: m < 64 -> W_hh[:, m],
+// m = 64 + c -> W_ih[:, c].
+__global__ void lstm16_wgrad_reduce_kernel(const float* __restrict__ slices, int n_slices, int layer, int c_in,
+                                           const float* __restrict__ dbp, float* __restrict__ d_w_ih,
+                                           float* __restrict__ d_w_hh, float* __restrict__ d_b_ih, float* __restrict__ d_b_hh) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;           // index in the slice layout
+    if (e < kTileM * kGateCols) {
+        float s = 0.f;
+        for (int i = 0; i < n_slices; ++i) s += slices[(size_t)i * (kTileM * kGateCols) + e];
+        const int x = e & 3, m = (e >> 2) & 127, rest = e >> 9;    // rest = (part*4 + j)*4 + vec
+        const int n = (rest >> 2) * 16 + (rest & 3) * 4 + x;       // gate-interleaved column
+        const int nat = (n & 3) * kHid + (n >> 2);
+        if (layer > 0) {
+            if (m < 64) d_w_ih[(size_t)nat * kHid + m] = s;
+            else d_w_hh[(size_t)nat * kHid + (m - 64)] = s;
+        } else {
+            if (m < 64) d_w_hh[(size_t)nat * kHid + m] = s;
+            else if (m - 64 < c_in) d_w_ih[(size_t)nat * c_in + (m - 64)] = s;
+        }
+    }
+    if (e < kGateCols) {
+        const int nat = (e & 3) * kHid + (e >> 2);
+        d_b_ih[nat] = dbp[e];
+        d_b_hh[nat] = dbp[e];
+    }
+}
+
+}  // namespace
+
+namespace stmgcn {
+
+typedef CUresult (*EncodeTiledFn16)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn16 encode_fn16() {
+    static EncodeTiledFn16 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn16)sym;
+    }
+    return fn;
+}
+// (slices, rows, 64) bf16 plane tensor, box = 1 x 128 x 64, 128-byte swizzle (rows past the end read as zeros)
+bool make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int64_t slices) {
+    EncodeTiledFn16 fn = encode_fn16();
+    if (fn == nullptr) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)kHid, (cuuint64_t)rows, (cuuint64_t)slices};
+    const cuuint64_t strides[2] = {(cuuint64_t)kHid * 2, (cuuint64_t)rows * kHid * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)kHid, (cuuint32_t)kTileM, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int32_t set_smem_attr(const void* fn, size_t bytes) {
+    // per device (the attribute is per device): cheap, so set unconditionally per launch site on first use per device
+    static bool done[64][8] = {};
+    static const void* fns[8] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int slot = -1;
+    for (int i = 0; i < 8; ++i) {
+        if (fns[i] == fn) { slot = i; break; }
+        if (fns[i] == nullptr) { fns[i] = fn; slot = i; break; }
+    }
+    if (slot < 0 || dev < 0 || dev >= 64 || !done[dev][slot]) {
+        STMGCN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        if (slot >= 0 && dev >= 0 && dev < 64) done[dev][slot] = true;
+    }
+    return 0;
+}
+
+}  // namespace stmgcn
+
+extern "C" int32_t stmgcn_lstm16_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                      int32_t layer, int32_t c_in, void* wimg, float* bias, float* wih_t, void* stream) {
+    STMGCN_REQUIRE(w_ih && w_hh && b_ih && b_hh && wimg && bias, STMGCN_ERR_ARG, "lstm16_pack: null pointer");
+    STMGCN_REQUIRE(layer >= 0 && c_in >= 1 && c_in <= kMaxC, STMGCN_ERR_SHAPE, "lstm16_pack: layer=%d c_in=%d", layer, c_in);
+    STMGCN_REQUIRE(layer > 0 || wih_t != nullptr, STMGCN_ERR_ARG, "lstm16_pack: layer 0 needs wih_t");
+    lstm16_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w_ih, w_hh, b_ih, b_hh, layer, c_in, (uint8_t*)wimg, bias, wih_t);
+    count_launch();
+    return check_launch("lstm16_pack");
+}
+
+extern "C" int32_t stmgcn_lstm16_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t c_in,
+                                          int64_t b_inner, int32_t planes, const float* xo, const float* s_gate,
+                                          const void* const* wimg, const float* const* bias, const float* wih_t,
+                                          const void* h0p, const float* c0, void* hp, float* cs, float* h_top,
+                                          float* h_n, void* stream) {
+    STMGCN_REQUIRE(xo && s_gate && wimg && bias && wih_t && hp && cs, STMGCN_ERR_ARG, "lstm16_step_fwd: null pointer");
+    STMGCN_REQUIRE(planes == 1 || planes == 2, STMGCN_ERR_ARG, "lstm16_step_fwd: planes=%d", planes);
+    STMGCN_REQUIRE(t >= 0 && t < t_len && n_layers >= 1 && n_layers <= 8 && rows > 0 && c_in >= 1 && c_in <= kMaxC && b_inner > 0,
+                   STMGCN_ERR_SHAPE, "lstm16_step_fwd: t=%d T=%d L=%d rows=%lld C=%d", t, t_len, n_layers, (long long)rows, c_in);
+    STMGCN_REQUIRE(rows <= 0x7fffff00LL, STMGCN_ERR_SHAPE, "lstm16_step_fwd: rows=%lld too large", (long long)rows);
+    STMGCN_REQUIRE((h0p == nullptr) == (c0 == nullptr), STMGCN_ERR_ARG, "lstm16_step_fwd: h0p and c0 go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_tiles = (int)ceil_div(rows, kTileM);
+    const int64_t rows_pad = (int64_t)n_tiles * kTileM;
+    const int64_t plane_elems = rows * kHid;                       // bf16 elements per plane
+    const int64_t cslice = rows_pad * kHid;
+    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_fwd_kernel<2> : (const void*)lstm16_fwd_kernel<1>, kFSmem)) return rc;
+    CUtensorMap hp_map, h0_map;
+    STMGCN_REQUIRE(make_plane_map(&hp_map, hp, rows, (int64_t)n_layers * t_len * planes), STMGCN_ERR_STATE,
+                   "lstm16_step_fwd: cuTensorMapEncodeTiled failed (hp)");
+    if (h0p != nullptr)
+        STMGCN_REQUIRE(make_plane_map(&h0_map, h0p, rows, (int64_t)n_layers * planes), STMGCN_ERR_STATE,
+                       "lstm16_step_fwd: cuTensorMapEncodeTiled failed (h0p)");
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    for (int l = 0; l < n_layers; ++l) {
+        STMGCN_REQUIRE(wimg[l] && bias[l], STMGCN_ERR_ARG, "lstm16_step_fwd: wimg/bias[%d] null", l);
+        Fwd16Params p;
+        memset(&p, 0, sizeof(p));
+        int ns = 0;
+        if (l > 0) {                                               // segment: h of the layer below at this step
+            p.amap[ns] = hp_map;
+            p.aslice[ns] = ((l - 1) * t_len + t) * planes;
+            ++ns;
+        }
+        if (t > 0) {                                               // segment: this layer's h of the previous step
+            p.amap[ns] = hp_map;
+            p.aslice[ns] = (l * t_len + t - 1) * planes;
+            ++ns;
+        } else if (h0p != nullptr) {
+            p.amap[ns] = h0_map;
+            p.aslice[ns] = l * planes;
+            ++ns;
+        }
+        p.nseg = ns;
+        // the weight image holds [seg0 hi | seg0 lo | seg1 hi | seg1 lo]; at t = 0 without h0 the h_prev segment is absent:
+        // layers > 0 then use only seg 0 (W_ih), layer 0 has no MMA at all
+        p.wimg = (const uint8_t*)wimg[l];
+        p.bias = bias[l];
+        p.wih = (l == 0) ? wih_t : nullptr;
+        p.xo = xo;
+        p.sg = s_gate;
+        p.c_in = c_in;
+        p.t = t;
+        p.t_len = t_len;
+        p.b_inner = b_inner;
+        p.c_prev = t > 0 ? cs + (int64_t)(l * t_len + t - 1) * cslice : (c0 ? c0 + (int64_t)l * cslice : nullptr);
+        p.c_out = cs + (int64_t)(l * t_len + t) * cslice;
+        uint16_t* hbase = (uint16_t*)hp + (int64_t)(l * t_len + t) * planes * plane_elems;
+        p.h_hi = hbase;
+        p.h_lo = planes == 2 ? hbase + plane_elems : nullptr;
+        p.h_f32 = nullptr;
+        if (t == t_len - 1) {
+            if (h_n != nullptr) p.h_f32 = h_n + (int64_t)l * rows * kHid;
+            else if (l == n_layers - 1) p.h_f32 = h_top;
+        }
+        p.rows = rows;
+        p.n_tiles = n_tiles;
+        if (planes == 2) lstm16_fwd_kernel<2><<<grid, kFThreads, kFSmem, st>>>(p);
+        else lstm16_fwd_kernel<1><<<grid, kFThreads, kFSmem, st>>>(p);
+        count_launch();
+        if (int32_t rc = check_launch("lstm16_fwd")) return rc;
+    }
+    return 0;
+}
+
+extern "C" int32_t stmgcn_lstm16_grid(int64_t rows) {
+    const int64_t n_tiles = ceil_div(rows, kTileM);
+    return (int32_t)(n_tiles < sm_count() ? n_tiles : sm_count());
+}
+
+extern "C" int32_t stmgcn_lstm16_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t c_in,
+                                          int64_t b_inner, int32_t planes, const float* xo, const float* s_gate,
+                                          const void* const* wimg, const float* const* bias, const float* wih_t,
+                                          const void* h0p, const float* c0, const void* hp, const float* cs,
+                                          const float* d_top, float* dh_rec, float* dc, float* dx_work, float* d_s,
+                                          float* const* dbp, float* dw_scratch, void* stream) {
+    STMGCN_REQUIRE(xo && s_gate && wimg && bias && wih_t && hp && cs && d_top && dh_rec && dc && dx_work && d_s && dbp && dw_scratch,
+                   STMGCN_ERR_ARG, "lstm16_step_bwd: null pointer");
+    STMGCN_REQUIRE(planes == 1 || planes == 2, STMGCN_ERR_ARG, "lstm16_step_bwd: planes=%d", planes);
+    STMGCN_REQUIRE(t >= 0 && t < t_len && n_layers >= 1 && n_layers <= 8 && rows > 0 && c_in >= 1 && c_in <= kMaxC && b_inner > 0,
+                   STMGCN_ERR_SHAPE, "lstm16_step_bwd: t=%d T=%d L=%d rows=%lld C=%d", t, t_len, n_layers, (long long)rows, c_in);
+    STMGCN_REQUIRE(rows <= 0x7fffff00LL, STMGCN_ERR_SHAPE, "lstm16_step_bwd: rows=%lld too large", (long long)rows);
+    STMGCN_REQUIRE((h0p == nullptr) == (c0 == nullptr), STMGCN_ERR_ARG, "lstm16_step_bwd: h0p and c0 go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_tiles = (int)ceil_div(rows, kTileM);
+    const int64_t cslice = (int64_t)n_tiles * kTileM * kHid;
+    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_bwd_kernel<2> : (const void*)lstm16_bwd_kernel<1>, kBSmem)) return rc;
+    CUtensorMap hp_map, h0_map;
+    STMGCN_REQUIRE(make_plane_map(&hp_map, hp, rows, (int64_t)n_layers * t_len * planes), STMGCN_ERR_STATE,
+                   "lstm16_step_bwd: cuTensorMapEncodeTiled failed (hp)");
+    if (h0p != nullptr)
+        STMGCN_REQUIRE(make_plane_map(&h0_map, h0p, rows, (int64_t)n_layers * planes), STMGCN_ERR_STATE,
+                       "lstm16_step_bwd: cuTensorMapEncodeTiled failed (h0p)");
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    for (int l = n_layers - 1; l >= 0; --l) {
+        STMGCN_REQUIRE(wimg[l] && bias[l] && dbp[l], STMGCN_ERR_ARG, "lstm16_step_bwd: wimg/bias/dbp[%d] null", l);
+        Bwd16Params p;
+        memset(&p, 0, sizeof(p));
+        int ns = 0;
+        if (l > 0) {
+            p.amap[ns] = hp_map;
+            p.aslice[ns] = ((l - 1) * t_len + t) * planes;
+            ++ns;
+        }
+        if (t > 0) {
+            p.amap[ns] = hp_map;
+            p.aslice[ns] = (l * t_len + t - 1) * planes;
+            ++ns;
+        } else if (h0p != nullptr) {
+            p.amap[ns] = h0_map;
+            p.aslice[ns] = l * planes;
+            ++ns;
+        }
+        p.nseg = ns;
+        p.layer0 = (l == 0) ? 1 : 0;
+        p.wimg = (const uint8_t*)wimg[l];
+        p.bias = bias[l];
+        p.wih = (l == 0) ? wih_t : nullptr;
+        p.xo = xo;
+        p.sg = s_gate;
+        p.d_s = d_s;
+        p.c_in = c_in;
+        p.t = t;
+        p.t_len = t_len;
+        p.b_inner = b_inner;
+        p.c_prev = t > 0 ? cs + (int64_t)(l * t_len + t - 1) * cslice : (c0 ? c0 + (int64_t)l * cslice : nullptr);
+        p.dh_in = (l == n_layers - 1) ? (t == t_len - 1 ? d_top : nullptr) : dx_work;
+        p.dh_rec = dh_rec + (int64_t)l * cslice;
+        p.dc = dc + (int64_t)l * cslice;
+        p.dx_out = l > 0 ? dx_work : nullptr;
+        p.first = (t == t_len - 1) ? 1 : 0;
+        p.store_dh = (t > 0 || h0p != nullptr) ? 1 : 0;
+        p.dbp = dbp[l];
+        p.dw_slice = dw_scratch + (size_t)l * grid * (kTileM * kGateCols);
+        p.dw_first = (t == t_len - 1) ? 1 : 0;
+        if (l > 0) {
+            p.flush_lo = 1;
+            p.flush_hi = (ns == 2) ? 1 : 0;
+        } else {
+            p.flush_lo = (ns == 1) ? 1 : 0;
+            p.flush_hi = 1;
+        }
+        p.rows = rows;
+        p.n_tiles = n_tiles;
+        if (planes == 2) lstm16_bwd_kernel<2><<<grid, kBThreads, kBSmem, st>>>(p);
+        else lstm16_bwd_kernel<1><<<grid, kBThreads, kBSmem, st>>>(p);
+        count_launch();
+        if (int32_t rc = check_launch("lstm16_bwd")) return rc;
+    }
+    return 0;
+}
+
+extern "C" int32_t stmgcn_lstm16_wgrad_reduce(int32_t layer, int32_t c_in, int32_t n_slices, const float* slices,
+                                              const float* dbp, float* d_w_ih, float* d_w_hh, float* d_b_ih,
+                                              float* d_b_hh, void* stream) {
+    STMGCN_REQUIRE(slices && dbp && d_w_ih && d_w_hh && d_b_ih && d_b_hh, STMGCN_ERR_ARG, "lstm16_wgrad_reduce: null pointer");
+    STMGCN_REQUIRE(layer >= 0 && n_slices >= 1 && c_in >= 1 && c_in <= kMaxC, STMGCN_ERR_SHAPE, "lstm16_wgrad_reduce: bad sizes");
+    lstm16_wgrad_reduce_kernel<<<(kTileM * kGateCols) / 256, 256, 0, (cudaStream_t)stream>>>(slices, n_slices, layer, c_in, dbp,
+                                                                                        d_w_ih, d_w_hh, d_b_ih, d_b_hh);
+    count_launch();
+    return check_launch("lstm16_wgrad_reduce");
+}

@@ -45,6 +45,14 @@ SIGNATURES = [
                                        _P, POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                        POINTER(c_void_p), c_int32, _P]),
     ("stmgcn_lstm_wgrad", c_int32, [c_int32, c_int32, c_int32, c_int64, c_int32, _P, _P, _P, _P, c_int32, _P]),
+    ("stmgcn_lstm16_pack", c_int32, [_P, _P, _P, _P, c_int32, c_int32, _P, _P, _P, _P]),
+    ("stmgcn_lstm16_step_fwd", c_int32, [c_int32, c_int32, c_int32, c_int64, c_int32, c_int64, c_int32, _P, _P,
+                                         POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("stmgcn_lstm16_grid", c_int32, [c_int64]),
+    ("stmgcn_lstm16_step_bwd", c_int32, [c_int32, c_int32, c_int32, c_int64, c_int32, c_int64, c_int32, _P, _P,
+                                         POINTER(c_void_p), POINTER(c_void_p), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                         POINTER(c_void_p), _P, _P]),
+    ("stmgcn_lstm16_wgrad_reduce", c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P]),
     ("stmgcn_fuse_out_fwd", c_int32, [POINTER(c_void_p), c_int32, c_int64, c_int64, c_int32, c_int32, _P, _P,
                                       _P, _P, _P]),
     ("stmgcn_fuse_out_bwd", c_int32, [_P, _P, c_int64, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P]),

@@ -15,6 +15,7 @@ Functions (reference lines they replace):
 from __future__ import annotations
 
 import os
+from collections import OrderedDict
 from typing import List, Optional, Sequence
 
 import torch
@@ -321,6 +322,143 @@ def _unpack_lstm_grads(dwx, dwp, dbp, n_layers: int, hid: int, c_in: int):
     return grads
 
 
+# --------------------------------------------------------------------------------------------------
+# bf16-plane LSTM path (H = 64): resident weight images cached per parameter version
+# --------------------------------------------------------------------------------------------------
+_PLANES = int(os.environ.get("STMGCN_LSTM_PLANES", "2"))     # 2: 3xBF16 (fp32-grade); 1: single-pass bf16 arithmetic
+
+
+def lstm_planes() -> int:
+    return _PLANES
+
+
+def set_lstm_planes(planes: int) -> None:
+    """2 = hi + lo bf16 planes, three tensor-core passes (fp32-grade, the 1e-4 parity mode);
+    1 = hi plane only, one pass (the arithmetic of the bf16-quoted BASELINE configs)."""
+    global _PLANES
+    if planes not in (1, 2):
+        raise ValueError(planes)
+    _PLANES = planes
+
+
+_W16_CACHE: "OrderedDict" = OrderedDict()
+_W16_MAX = 24
+
+
+def _lstm16_images(weights: Sequence[torch.Tensor], n_layers: int, c_in: int):
+    """Operand images of the shared LSTM's parameters for the bf16-plane kernels (stmgcn_lstm16_pack), cached on
+    (storage, in-place version) of every parameter: re-packed only after an optimizer step changed them.  During CUDA
+    graph capture the cache is bypassed so the pack kernels become part of the graph (replays see updated weights)."""
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = tuple((w.data_ptr(), w._version) for w in weights) + (c_in, str(weights[0].device))
+    if not capturing:
+        hit = _W16_CACHE.get(key)
+        if hit is not None:
+            _W16_CACHE.move_to_end(key)
+            torch.cuda.current_stream().wait_event(hit["event"])
+            return hit
+    dev = weights[0].device
+    wimg = [torch.empty(65536 if l == 0 else 131072, dtype=torch.uint8, device=dev) for l in range(n_layers)]
+    bias = [torch.empty(256, dtype=torch.float32, device=dev) for _ in range(n_layers)]
+    wih_t = torch.empty(c_in * 256, dtype=torch.float32, device=dev)
+    st = _stream()
+    for l in range(n_layers):
+        w_ih, w_hh, b_ih, b_hh = weights[4 * l:4 * l + 4]
+        _lib.check(L.stmgcn_lstm16_pack(w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), l, c_in,
+                                        wimg[l].data_ptr(), bias[l].data_ptr(), wih_t.data_ptr() if l == 0 else None, st),
+                   "lstm16_pack")
+    entry = dict(wimg=wimg, bias=bias, wih_t=wih_t, wimg_arr=_lib.ptr_array([v.data_ptr() for v in wimg]),
+                 bias_arr=_lib.ptr_array([v.data_ptr() for v in bias]),
+                 keep=list(weights))            # keeps the storages alive: a recycled data_ptr can never alias the key
+    if not capturing:
+        ev = torch.cuda.Event()
+        ev.record()
+        entry["event"] = ev
+        _W16_CACHE[key] = entry
+        while len(_W16_CACHE) > _W16_MAX:
+            _W16_CACHE.popitem(last=False)
+    return entry
+
+
+def to_planes(x: torch.Tensor, planes: int) -> torch.Tensor:
+    """(..., R, 64) fp32 -> (..., planes, R, 64) bf16: hi = bf16(x), lo = bf16(x - hi)."""
+    hi = x.to(torch.bfloat16)
+    if planes == 1:
+        return hi.unsqueeze(-3).contiguous()
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo], dim=-3).contiguous()
+
+
+def _lstm16_forward(xo, s_gate, h0c, c0c, n_layers, want_state, weights, planes, keep_tape):
+    """Forward of the bf16-plane path.  Returns (h_top (N,B,64), h_n, c_n, tape dict or None)."""
+    n, b, t_len, c_in = xo.shape
+    rows = n * b
+    dev = xo.device
+    rows_pad = ((rows + 127) // 128) * 128
+    img = _lstm16_images(weights, n_layers, c_in)
+    hp = torch.empty((n_layers, t_len, planes, rows, 64), device=dev, dtype=torch.bfloat16)
+    cs = torch.empty((n_layers, t_len, rows_pad, 64), device=dev, dtype=torch.float32)
+    h0p = to_planes(h0c, planes) if h0c is not None else None        # (L, P, R, 64)
+    c0b = to_blocked(c0c) if c0c is not None else None
+    if want_state:
+        h_n = torch.empty((n_layers, rows, 64), device=dev, dtype=torch.float32)
+        h_top = h_n[n_layers - 1]
+    else:
+        h_n = None
+        h_top = torch.empty((rows, 64), device=dev, dtype=torch.float32)
+    st = _stream()
+    for t in range(t_len):
+        _lib.check(L.stmgcn_lstm16_step_fwd(t, t_len, n_layers, rows, c_in, b, planes, xo.data_ptr(), s_gate.data_ptr(),
+                                            img["wimg_arr"], img["bias_arr"], img["wih_t"].data_ptr(), _p(h0p), _p(c0b),
+                                            hp.data_ptr(), cs.data_ptr(), h_top.data_ptr(), _p(h_n), st),
+                   "lstm16_step_fwd")
+    if want_state:
+        c_n = from_blocked(cs[:, t_len - 1], rows)
+    else:
+        h_n = c_n = torch.empty(0, device=dev, dtype=torch.float32)
+    tape = dict(hp=hp, cs=cs, h0p=h0p, c0b=c0b, img=img) if keep_tape else None
+    return h_top.view(n, b, 64), h_n, c_n, tape
+
+
+def _lstm16_backward(xo, s_gate, tape, n_layers, planes, d_top):
+    """BPTT of the bf16-plane path: one fused kernel per layer-step (gate recompute + pointwise + data gradient + weight
+    gradient, stmgcn_lstm16_step_bwd), then one reduction per layer.  Returns (d_s, [native nn.LSTM gradients])."""
+    n, b, t_len, c_in = xo.shape
+    rows = n * b
+    dev = xo.device
+    rows_pad = ((rows + 127) // 128) * 128
+    img = tape["img"]
+    torch.cuda.current_stream().wait_event(img["event"]) if "event" in img else None
+    d_top_b = to_blocked(_f32c(d_top).view(rows, 64))
+    dh_rec = torch.empty((n_layers, rows_pad, 64), device=dev, dtype=torch.float32)
+    dc = torch.empty((n_layers, rows_pad, 64), device=dev, dtype=torch.float32)
+    dx_work = torch.empty((rows_pad, 64), device=dev, dtype=torch.float32)
+    d_s = torch.zeros((b, t_len), device=dev, dtype=torch.float32)
+    dbp = torch.zeros((n_layers, 256), device=dev, dtype=torch.float32)
+    grid = int(L.stmgcn_lstm16_grid(rows))
+    scratch = torch.empty((n_layers, grid, 128 * 256), device=dev, dtype=torch.float32)
+    dbp_arr = _lib.ptr_array([dbp[l].data_ptr() for l in range(n_layers)])
+    st = _stream()
+    for t in range(t_len - 1, -1, -1):
+        _lib.check(L.stmgcn_lstm16_step_bwd(t, t_len, n_layers, rows, c_in, b, planes, xo.data_ptr(), s_gate.data_ptr(),
+                                            img["wimg_arr"], img["bias_arr"], img["wih_t"].data_ptr(), _p(tape["h0p"]),
+                                            _p(tape["c0b"]), tape["hp"].data_ptr(), tape["cs"].data_ptr(),
+                                            d_top_b.data_ptr(), dh_rec.data_ptr(), dc.data_ptr(), dx_work.data_ptr(),
+                                            d_s.data_ptr(), dbp_arr, scratch.data_ptr(), st), "lstm16_step_bwd")
+    grads = []
+    for l in range(n_layers):
+        in_l = c_in if l == 0 else 64
+        d_w_ih = torch.empty((256, in_l), device=dev, dtype=torch.float32)
+        d_w_hh = torch.empty((256, 64), device=dev, dtype=torch.float32)
+        d_b_ih = torch.empty(256, device=dev, dtype=torch.float32)
+        d_b_hh = torch.empty(256, device=dev, dtype=torch.float32)
+        _lib.check(L.stmgcn_lstm16_wgrad_reduce(l, c_in, grid, scratch[l].data_ptr(), dbp[l].data_ptr(), d_w_ih.data_ptr(),
+                                                d_w_hh.data_ptr(), d_b_ih.data_ptr(), d_b_hh.data_ptr(), st),
+                   "lstm16_wgrad_reduce")
+        grads += [d_w_ih, d_w_hh, d_b_ih, d_b_hh]
+    return d_s, grads
+
+
 class SharedLSTM(torch.autograd.Function):
     """h_top (N,B,H) of the shared multi-layer LSTM over rows r = n*B + b; input ``xo * s[b,t]``.
 
@@ -340,6 +478,18 @@ class SharedLSTM(torch.autograd.Function):
         h0c = _f32c(h0) if h0 is not None else None
         c0c = _f32c(c0) if c0 is not None else None
         need_grad = any(ctx.needs_input_grad)
+        ctx.planes16 = False
+        env16 = os.environ.get("STMGCN_LSTM16", "1")          # "0": first-generation kernels; "fwd": new forward only
+        if hid == 64 and lstm_path() == "tc" and c_in <= 4 and env16 != "0" and not (need_grad and env16 == "fwd"):
+            # second-generation kernels: bf16 hi/lo planes, resident weights, no gate tape (lstm16.cu)
+            planes = lstm_planes()
+            h_top, h_n, c_n, tape = _lstm16_forward(xo, s_gate, h0c, c0c, n_layers, want_state, weights, planes, need_grad)
+            ctx.mark_non_differentiable(h_n, c_n)
+            if need_grad:
+                ctx.planes16, ctx.tape16, ctx.planes = True, tape, planes
+                ctx.dims = (n, b, t_len, c_in, n_layers, hid)
+                ctx.save_for_backward(xo, s_gate)
+            return h_top, h_n, c_n
         wx, wp, bp, wpt = _pack_lstm(weights, n_layers, hid)
         # tensor-core kernels on every layer (H = 64, input_dim = 1): the cell-state tape and the backward workspaces are
         # tile-blocked so every 8-unit slice of a 128-row tile is one contiguous 4 KB run (see stmgcn_lstm_step_bwd)
@@ -388,6 +538,14 @@ class SharedLSTM(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_top, _dhn, _dcn):
+        if ctx.planes16:
+            xo, s_gate = ctx.saved_tensors
+            d_s, w_grads = _lstm16_backward(xo, s_gate, ctx.tape16, ctx.dims[4], ctx.planes, d_top)
+            return (None, d_s, None, None, None, None, None, *w_grads)
+        if getattr(ctx, "tape_consumed", False):
+            raise RuntimeError("SharedLSTM (first-generation kernels): the gate tape was overwritten in place by the first "
+                               "backward pass; a second backward over the same graph is not supported")
+        ctx.tape_consumed = True
         xo, s_gate, h0, c0, hs, cs, gates, wx, *rest = ctx.saved_tensors
         n, b, t_len, c_in, n_layers, hid = ctx.dims
         wpt, wimg_t = rest[:n_layers], rest[n_layers:]
