@@ -326,6 +326,8 @@ def run_ours(args, w):
             bucket.all_reduce_mean_()
             return loss
 
+    ms_step_local = [0.0]                  # this rank's own device time per step of the last timed() call
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -340,6 +342,7 @@ def run_ours(args, w):
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms_step_local[0] = float(ms.item()) / steps
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
@@ -357,6 +360,44 @@ def run_ours(args, w):
     ms_step = ms_total / args.steps
     units = b * world * w.n_regions * w.seq_len
     value = units / (ms_step * 1e-3)
+
+    # ---- correctness gate: the loss of the timed step against the fp64 oracle's value for these exact inputs ----------
+    # (tests/golden/bench_loss.json, written by oracle/make_bench_loss.py in the build container: SparseOracle.forward
+    # on the same seeded model and inputs).  A kernel that is fast but wrong at THIS size cannot print a number.
+    loss_val = float(step(x_d, y_d).item())
+    loss_check = {"loss": loss_val, "reference": None, "rel_err": None, "tolerance": 1e-4, "ok": None,
+                  "source": "tests/golden/bench_loss.json (fp64 sparse oracle, oracle/make_bench_loss.py)"}
+    table_path = os.path.join(REPO, "tests", "golden", "bench_loss.json")
+    ok_flag = 1.0
+    if os.path.exists(table_path):
+        with open(table_path) as fh:
+            table = json.load(fh)
+        ref_loss = table.get(f"{w.name}/batch{b}/rank{rank}")
+        if ref_loss is not None:
+            rel = abs(loss_val - ref_loss) / max(abs(ref_loss), 1e-30)
+            tol = 1e-4 if ops.lstm_planes() == 2 else 2e-2        # fp32-grade arithmetic / single-pass bf16
+            loss_check.update(reference=ref_loss, rel_err=rel, tolerance=tol, ok=bool(rel <= tol))
+            ok_flag = 1.0 if rel <= tol else 0.0
+    okt = torch.tensor([ok_flag], device=dev)
+    per_rank_ms = torch.zeros(world, device=dev)
+    per_rank_ms[rank] = ms_step_local[0]
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        dist.all_reduce(per_rank_ms, op=dist.ReduceOp.SUM)
+    if float(okt.item()) < 1.0:
+        raise RuntimeError(f"bench.py: loss check failed on some rank (rank {rank}: {loss_check}); refusing to report a number")
+    # the collective alone (CUDA events around the all-reduce of the flat gradient bucket, mean of 20)
+    allreduce_us = None
+    if world > 1:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        e0.record()
+        for _ in range(20):
+            bucket.all_reduce_mean_()
+        e1.record()
+        torch.cuda.synchronize()
+        allreduce_us = e0.elapsed_time(e1) / 20 * 1e3
 
     # ---- end to end: host (pinned) inputs through the public module API ------------------------------------
     e2e = None
@@ -476,26 +517,30 @@ def run_ours(args, w):
         runs = [lstm_once() for _ in range(3)]
         ms_f = sum(r[0] for r in runs) / len(runs)
         ms_b = sum(r[1] for r in runs) / len(runs)
-        u = rows * hid * 4                                    # one (rows, H) fp32 array
-        fwd_u = bwd_u = wg_u = 0
+        u = rows * hid * 4                                    # one (rows, H) array at 4 bytes per value (fp32, or bf16 hi + lo)
+        planes = ops.lstm_planes()
+        hu = planes / 2.0                                     # a hidden-state array: 2 bf16 planes = 1 unit, 1 plane = 0.5
+        fwd_u = bwd_u = 0
         for l in range(lyr):
             for t in range(t_len):
-                fwd_u += (1 if l > 0 else 0) + (2 if t > 0 else 0) + 2 + 4          # h_below, h/c_{t-1} | h, c, gate tape
+                # forward: h_below planes, h_{t-1} planes + c_{t-1} | h planes, c
+                fwd_u += (hu if l > 0 else 0) + ((hu + 1) if t > 0 else 0) + hu + 1
+                # fused backward: A planes (h_below, h_{t-1}), c_{t-1}, dh_in, dh_rec + dc in | dc, dh_rec, dx_below out
                 dh_in = 1 if l < lyr - 1 else (1 if t == t_len - 1 else 0)
-                bwd_u += 4 + 1 + (1 if t > 0 else 0) + (2 if t < t_len - 1 else 0) + dh_in     # tape, c_t, c_prev, dh_rec/dc
-                bwd_u += 4 + 2 + (1 if l > 0 else 0)                                           # dA, dc, dh_rec, dx_below
-                wg_u += 4 + (1 if l > 0 else 0) + (1 if t > 0 else 0)                          # dA, h_below, h_{t-1}
+                bwd_u += (hu if l > 0 else 0) + ((hu + 1) if t > 0 else 0) + dh_in + (2 if t < t_len - 1 else 0)
+                bwd_u += 1 + (1 if t > 0 else 0) + (1 if l > 0 else 0)
         fwd_b = fwd_u * u + rows * t_len * 4
-        bwd_b = (bwd_u + wg_u) * u + rows * t_len * 4
+        bwd_b = bwd_u * u + rows * t_len * 4
         roofline_lstm = {
             "scope": f"shared {lyr}-layer LSTM of ONE graph branch (rows = N*B = {rows}, H = {hid}, T = {t_len}), timed alone with "
-                     "CUDA events, mean of 3 after 2 warm-ups; algorithmic bytes count every (rows, H) fp32 array a layer-step "
-                     "must read or write once (h_below, h/c_{t-1}, h, c, 4H gate tape; backward: tape, c_t, c_{t-1}, dh, dc, "
-                     "dA, dx; weight gradients: dA + inputs); weights and biases are negligible",
-            "bound": "hbm", "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "forward": {"kernel": "lstm_cell_tc_kernel", "launches": runs[0][2], "ms": ms_f, "algorithmic_bytes": fwd_b,
+                     "CUDA events, mean of 3 after 2 warm-ups; algorithmic bytes count every (rows, H) array a layer-step must "
+                     f"read or write once at 4 B per value ({planes} bf16 plane(s) per hidden state): forward h_below, h/c_(t-1) in, "
+                     "h, c out; fused backward (gate recompute + BPTT pointwise + data and weight gradients in one kernel): "
+                     "h_below, h/c_(t-1), dh_in, dh_rec, dc in, dc, dh_rec, dx_below out; weights are resident / L2",
+            "bound": "hbm", "peak": pk["hbm_gbs"], "unit": "GB/s", "planes": planes,
+            "forward": {"kernel": "lstm16_fwd_kernel", "launches": runs[0][2], "ms": ms_f, "algorithmic_bytes": fwd_b,
                         "achieved": fwd_b / (ms_f * 1e-3) / 1e9, "frac": fwd_b / (ms_f * 1e-3) / 1e9 / pk["hbm_gbs"]},
-            "backward": {"kernel": "lstm_bwd_tc_kernel + lstm_wgrad_tc_kernel", "launches": runs[0][3], "ms": ms_b,
+            "backward": {"kernel": "lstm16_bwd_kernel (+ lstm16_wgrad_reduce_kernel)", "launches": runs[0][3], "ms": ms_b,
                          "algorithmic_bytes": bwd_b, "achieved": bwd_b / (ms_b * 1e-3) / 1e9,
                          "frac": bwd_b / (ms_b * 1e-3) / 1e9 / pk["hbm_gbs"]}}
         del xo, s_gate, wts, d_top
@@ -508,9 +553,15 @@ def run_ours(args, w):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(w, world, b), cuda_graph=use_graph), "clocks": clocks,
-                "gpu_launches": int(launches),
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if ops.lstm_planes() == 2 else "bf16", "data": "synthetic",
+                "config": dict(workload_config(w, world, b), cuda_graph=use_graph,
+                               arithmetic=("fp32 state and accumulation; tensor-core products as 3-pass bf16 hi/lo planes "
+                                           "(3xBF16, fp32-grade)" if ops.lstm_planes() == 2 else
+                                           "fp32 state and accumulation; single-pass bf16 tensor-core products")),
+                "clocks": clocks,
+                "gpu_launches": int(launches), "loss_check": loss_check,
+                "per_rank_ms_per_step": [float(v) for v in per_rank_ms.tolist()], "allreduce_us": allreduce_us,
                 "e2e": e2e, "roofline": roofline, "roofline_lstm": roofline_lstm, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -89,9 +89,9 @@ int32_t stmgcn_obs_to_node_major(const float* obs, float* xo, float* xt, int64_t
 int32_t stmgcn_proj_fwd(const float* s, int64_t stride_k, int32_t ks, int64_t rows, int32_t p,
                         const float* w, const float* bias, int32_t q, int32_t act, float* out,
                         float* pool, int64_t b_inner, const float* wimg, void* stream);
-/* Tensor-core operand images of W (ks*64, 64) for p = q = 64, ks <= 4 (3xTF32, see stmgcn_lstm_pack_tc):
- * img_fwd: ks*64*64*2 floats; img_bwd (may be NULL): 2*2*256*32 floats, ZERO-FILLED by the caller (rows beyond
- * ks*64 stay zero).  Passing wimg / wimg_t != NULL to stmgcn_proj_fwd / _bwd selects the tcgen05 kernels when
+/* Tensor-core operand images of W (ks*64, 64) for p = q = 64, ks <= 8 (3xTF32, see stmgcn_lstm_pack_tc):
+ * img_fwd: ks*64*64*2 floats; img_bwd (may be NULL): one 2*2*256*32-float image per group of 4 supports (two images
+ * when ks > 4), ZERO-FILLED by the caller (rows beyond ks*64 stay zero).  Passing wimg / wimg_t != NULL to stmgcn_proj_fwd / _bwd selects the tcgen05 kernels when
  * p = q = 64 (and, for the backward, a full d_out and u are given); otherwise the exact-FFMA kernels run. */
 int32_t stmgcn_proj_pack_tc(const float* w, int32_t ks, float* img_fwd, float* img_bwd, void* stream);
 /* backward of the projection.  dZ = dOut (.) [out > 0] (act = RELU) with dOut either a full (rows, q)

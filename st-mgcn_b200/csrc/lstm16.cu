@@ -49,6 +49,43 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, in
                  :: "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// ---- LSTM cell with 8 MUFU operations instead of 10 ------------------------------------------------------------
+// sigmoid(v) = 1 / (1 + e^-v), tanh(v) = (1 - e^-2v) / (1 + e^-2v).  Five exponentials per cell are unavoidable (i, f, g, o,
+// tanh(c)); the five reciprocals are not: reciprocals of PRODUCTS of two (1 + e) terms serve two activations at once.
+// Arguments are clamped (sigmoid +-30, tanh +-15: the clamped values differ from the exact ones by < 1e-13) so that a
+// product of two (1 + e^30) terms stays far below the fp32 overflow threshold.  The cell epilogue is MUFU-bound
+// (16 MUFU results per clock and SM), so this is 20 % off its critical resource.
+__device__ __forceinline__ float exp_neg_(float v) { return ex2_ftz_(-1.4426950408889634f * fminf(fmaxf(v, -30.f), 30.f)); }
+__device__ __forceinline__ float exp_neg2_(float v) { return ex2_ftz_(-2.8853900817779268f * fminf(fmaxf(v, -15.f), 15.f)); }
+// forward: pre-activations (i, f, g, o) and c_{t-1} -> c_t, h_t
+__device__ __forceinline__ void lstm_cell_fwd8(float pi, float pf, float pg, float po, float cp, float& c, float& h) {
+    const float ei = exp_neg_(pi), ef = exp_neg_(pf), eg = exp_neg2_(pg), eo = exp_neg_(po);
+    const float ig = (1.f - eg) * rcp_ftz_((1.f + ei) * (1.f + eg));          // sigmoid(pi) * tanh(pg)
+    c = fmaf(rcp_ftz_(1.f + ef), cp, ig);
+    const float ec = exp_neg2_(c);
+    h = (1.f - ec) * rcp_ftz_((1.f + eo) * (1.f + ec));                      // sigmoid(po) * tanh(c)
+}
+// backward recompute: all four gate activations, c_t and tanh(c_t)
+__device__ __forceinline__ void lstm_cell_gates8(float pi, float pf, float pg, float po, float cp, float& gi, float& gf,
+                                                 float& gg, float& go, float& tc) {
+    const float ei = 1.f + exp_neg_(pi), ef = 1.f + exp_neg_(pf), eo = 1.f + exp_neg_(po);
+    const float eg = exp_neg2_(pg);
+    const float r1 = rcp_ftz_(ei * (1.f + eg));
+    const float r2 = rcp_ftz_(ef * eo);
+    gi = r1 * (1.f + eg);
+    gg = (1.f - eg) * (r1 * ei);
+    gf = r2 * eo;
+    go = r2 * ef;
+    const float ec = exp_neg2_(fmaf(gf, cp, gi * gg));
+    tc = (1.f - ec) * rcp_ftz_(1.f + ec);
+}
+
+// L2 prefetch of a tensor-map box (no shared memory, no barrier): the later TMA load of the same box finds it in L2
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 :: "l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // =====================================================================================================
 // forward
 // =====================================================================================================
@@ -92,7 +129,9 @@ struct Fwd16Params {
 template <int PLANES>
 __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_constant__ Fwd16Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would make every access through
+    // `smem` a generic LD/ST/ATOM instead of LDS/STS/ATOMS: ncu showed the bias loads as long-scoreboard stalls)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* wsm = smem;                                           // resident weight tiles
     uint8_t* stages = smem + 4 * (size_t)kWTileBytes;
     F16Tail* tail = (F16Tail*)(stages + (size_t)kFStages * kATileBytes);
@@ -109,7 +148,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tail->tmem_full[a], 1);
-            mbar_init(&tail->tmem_empty[a], kFEpiWarps * 32);
+            mbar_init(&tail->tmem_empty[a], kFEpiWarps);       // one arrival per epilogue warp
         }
         mbar_init(&tail->w_full, 1);
         fence_barrier_init();
@@ -126,6 +165,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
 
     if (warp == kProdWarp) {
         // ===================== producer: resident weights once, then the A planes of every tile =====================
+        TC_PROF_DECL
         if (lane == 0 && p.nseg > 0) {
             mbar_arrive_expect_tx(&tail->w_full, (uint32_t)(p.nseg * PLANES * kWTileBytes));
             for (int s = 0; s < p.nseg; ++s)
@@ -135,28 +175,32 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
             uint32_t it = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int tile = blockIdx.x + i * gridDim.x;
+                if (p.c_prev != nullptr && i + 2 < my_tiles)     // c_{t-1} of the tile after next -> L2 (a tile is contiguous)
+                    prefetch_l2(p.c_prev + (int64_t)(tile + 2 * (int)gridDim.x) * kTileM * kHid, kTileM * kHid * 4);
                 for (int s = 0; s < p.nseg; ++s)
                     for (int pl = 0; pl < PLANES; ++pl, ++it) {
                         const int stg = it % kFStages;
                         const uint32_t ph = (it / kFStages) & 1;
-                        mbar_wait_raw(&tail->empty[stg], ph ^ 1);
+                        mbar_wait_p(&tail->empty[stg], ph ^ 1, 0);
                         mbar_arrive_expect_tx(&tail->full[stg], kATileBytes);
                         tma_load_3d(stages + (size_t)stg * kATileBytes, &p.amap[s], 0, tile * kTileM, p.aslice[s] + pl,
                                     &tail->full[stg]);
                     }
             }
         }
+        TC_PROF_FLUSH(0, lane == 0)
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
+        TC_PROF_DECL
         if (p.nseg > 0) {
             constexpr uint32_t idesc = idesc_bf16(kTileM, kGateCols);
-            mbar_wait_raw(&tail->w_full, 0);
+            mbar_wait_p(&tail->w_full, 0, 0);
             tc_fence_after();
             uint32_t it = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int a = i & 1;
                 const uint32_t aph = (uint32_t)(i >> 1) & 1;
-                mbar_wait_raw(&tail->tmem_empty[a], aph ^ 1);
+                mbar_wait_p(&tail->tmem_empty[a], aph ^ 1, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)a * kGateCols;
                 for (int s = 0; s < p.nseg; ++s) {
@@ -165,7 +209,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                     {   // hi plane of the segment: against W hi (and W lo)
                         const int stg = it % kFStages;
                         const uint32_t ph = (it / kFStages) & 1;
-                        mbar_wait_raw(&tail->full[stg], ph);
+                        mbar_wait_p(&tail->full[stg], ph, 1);
                         tc_fence_after();
                         if (lane == 0) {
                             const uint64_t a_d = desc16_k(smem_u32(stages + (size_t)stg * kATileBytes));
@@ -185,7 +229,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                     if (PLANES == 2) {   // lo plane of the segment: against W hi
                         const int stg = it % kFStages;
                         const uint32_t ph = (it / kFStages) & 1;
-                        mbar_wait_raw(&tail->full[stg], ph);
+                        mbar_wait_p(&tail->full[stg], ph, 1);
                         tc_fence_after();
                         if (lane == 0) {
                             const uint64_t a_d = desc16_k(smem_u32(stages + (size_t)stg * kATileBytes));
@@ -202,31 +246,37 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                 __syncwarp();
             }
         }
+        TC_PROF_FLUSH(1, lane == 0)
     } else {
         // ===================== epilogue: LSTM cell =====================
+        TC_PROF_DECL
         // TMEM lane quadrant q = warp & 3 (rows 32q .. 32q+31 of the tile), column quarter part = warp >> 2
         // (gate columns 64*part .. +63 = units 16*part .. +15), four pieces of 16 columns = 4 units each
         const int q = warp & 3, part = warp >> 2;
         const bool l0 = p.wih != nullptr;
+        // c_{t-1} of this thread's row (16 units) lives in registers; the four floats a piece has just consumed are
+        // reloaded at once with the NEXT tile's values, so the loads are in flight for most of a tile (loading all 16 at the
+        // end of a tile exposed the full DRAM latency at the top of the next one: ncu showed 21 % of the samples there)
         float cpv[16];
-        float xs[kMaxC];
-        auto prefetch = [&](int tile_n) {       // c_{t-1} (and layer 0: x*s) of this thread's row, one tile ahead
+        float xs[kMaxC], xs_next[kMaxC];
+        auto load_c4 = [&](int tile_n, int j) {
+            const int64_t rn = (int64_t)tile_n * kTileM + q * 32 + lane;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.c_prev != nullptr && tile_n < p.n_tiles && rn < p.rows)
+                v = *reinterpret_cast<const float4*>(p.c_prev + ws_off(rn, part * 16 + 4 * j));
+            cpv[4 * j] = v.x; cpv[4 * j + 1] = v.y; cpv[4 * j + 2] = v.z; cpv[4 * j + 3] = v.w;
+        };
+        auto load_xs = [&](int tile_n, float (&dst)[kMaxC]) {
             const int64_t rn = (int64_t)tile_n * kTileM + q * 32 + lane;
             const bool ok = tile_n < p.n_tiles && rn < p.rows;
+            float sv = 0.f;
+            if (ok) sv = p.sg[(rn % p.b_inner) * p.t_len + p.t];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok && p.c_prev != nullptr) v = *reinterpret_cast<const float4*>(p.c_prev + ws_off(rn, part * 16 + 4 * j));
-                cpv[4 * j] = v.x; cpv[4 * j + 1] = v.y; cpv[4 * j + 2] = v.z; cpv[4 * j + 3] = v.w;
-            }
-            if (l0) {
-                float sv = 0.f;
-                if (ok) sv = p.sg[(rn % p.b_inner) * p.t_len + p.t];
-#pragma unroll
-                for (int c = 0; c < kMaxC; ++c) xs[c] = (ok && c < p.c_in) ? p.xo[(rn * p.t_len + p.t) * p.c_in + c] * sv : 0.f;
-            }
+            for (int c = 0; c < kMaxC; ++c) dst[c] = (ok && c < p.c_in) ? p.xo[(rn * p.t_len + p.t) * p.c_in + c] * sv : 0.f;
         };
-        prefetch((int)blockIdx.x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) load_c4((int)blockIdx.x, j);
+        if (l0) load_xs((int)blockIdx.x, xs);
         for (int i = 0; i < my_tiles; ++i) {
             const int tile = blockIdx.x + i * gridDim.x;
             const int a = i & 1;
@@ -234,7 +284,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
             const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
             const bool valid = r < p.rows;
             if (p.nseg > 0) {
-                mbar_wait_raw(&tail->tmem_full[a], aph);
+                mbar_wait(&tail->tmem_full[a], aph, 3);
                 tc_fence_after();
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * kGateCols + (uint32_t)part * 64;
@@ -268,9 +318,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                                 pg = fmaf(xs[c], wv.z, pg); po = fmaf(xs[c], wv.w, po);
                             }
                     }
-                    const float gi = sigmoidf_(pi), gf = sigmoidf_(pf), gg = tanhf_(pg), go = sigmoidf_(po);
-                    cn[u] = fmaf(gf, cpv[4 * pc + u], gi * gg);
-                    hn[u] = go * tanhf_(cn[u]);
+                    lstm_cell_fwd8(pi, pf, pg, po, cpv[4 * pc + u], cn[u], hn[u]);
                 }
                 if (PLANES == 2) {
                     split_bf16x2(hn[0], hn[1], hi[2 * pc], lo[2 * pc]);
@@ -284,10 +332,13 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                     if (p.h_f32 != nullptr)
                         *reinterpret_cast<float4*>(p.h_f32 + r * kHid + unit0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                 }
+                load_c4(tile + (int)gridDim.x, pc);             // this piece's registers are free: next tile's values
+                if (l0 && pc == 0) load_xs(tile + (int)gridDim.x, xs_next);
             }
-            if (p.nseg > 0) {          // all TMEM reads of this accumulator are done
-                tc_fence_before();
-                mbar_arrive(&tail->tmem_empty[a]);
+            if (p.nseg > 0) {          // all TMEM reads of this accumulator are done (one mbarrier arrival per warp: 512
+                tc_fence_before();     // per-thread arrivals are 512 serialised shared-memory atomics per tile)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tail->tmem_empty[a]);
             }
             if (valid) {
                 uint4* dh = reinterpret_cast<uint4*>(p.h_hi + r * kHid + part * 16);
@@ -299,8 +350,12 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                     dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
             }
-            prefetch(tile + (int)gridDim.x);
+            if (l0) {
+#pragma unroll
+                for (int c = 0; c < kMaxC; ++c) xs[c] = xs_next[c];
+            }
         }
+        TC_PROF_FLUSH(2, tid == 0)
     }
     tc_fence_before();
     __syncthreads();
@@ -404,10 +459,12 @@ struct Bwd16Params {
     int n_tiles;
 };
 
-template <int PLANES>
+template <int PLANES, bool L0>
 __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_constant__ Bwd16Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would make every access through
+    // `smem` a generic LD/ST/ATOM instead of LDS/STS/ATOMS: ncu showed the bias loads as long-scoreboard stalls)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_sm = smem;                                          // tiles 0..3: seg0 hi | seg0 lo | seg1 (aux) hi | seg1 (aux) lo
     uint8_t* w_sm = a_sm + 4 * (size_t)kATileBytes;                // weight chunk ring
     uint8_t* da_sm = w_sm + (size_t)kBWStages * kBWStageBytes;     // dA chunk: hi tile | lo tile
@@ -429,12 +486,12 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tail->r_full[b], 1);
-            mbar_init(&tail->r_empty[b], kCompThreads);
+            mbar_init(&tail->r_empty[b], kBCompWarps);         // one arrival per compute warp
         }
-        mbar_init(&tail->d_full, kCompThreads);
+        mbar_init(&tail->d_full, kBCompWarps);
         mbar_init(&tail->d_empty, 1);
         mbar_init(&tail->g_full, 1);
-        mbar_init(&tail->g_empty, kCompThreads);
+        mbar_init(&tail->g_empty, kBCompWarps);
         mbar_init(&tail->done, 1);
         fence_barrier_init();
     }
@@ -443,7 +500,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         tail->bias[i] = p.bias[i];
         tail->s_db[i] = 0.f;
     }
-    if (p.layer0) {
+    if (L0) {
         for (int i = tid; i < p.c_in * kGateCols; i += kBThreads) tail->wih[i] = p.wih[i];
         for (int i = tid; i < kBSgMax; i += kBThreads) tail->s_ds[i] = 0.f;
     }
@@ -452,30 +509,48 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = tail->tmem_base;
     const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const bool have_aux = p.layer0 != 0;
+    const bool have_aux = L0;
     // operand tiles of the weight-gradient GEMM (MN-major view): atom 0 and atom 1 along M = kd
     // layers > 0: atom 0 = h_below, atom 1 = h_prev (absent: duplicate of atom 0, rows 64.. are not flushed)
     // layer 0   : atom 0 = h_prev (absent at t = 0: duplicate of the auxiliary tile), atom 1 = auxiliary [x*s] tile
-    const uint32_t wg_a0 = (p.layer0 && p.nseg == 0) ? 2u : 0u;
-    const uint32_t wg_lbo = (p.layer0 ? (p.nseg == 0 ? 0u : 2u) : (p.nseg == 2 ? 2u : 0u)) * kATileBytes;
+    const uint32_t wg_a0 = (L0 && p.nseg == 0) ? 2u : 0u;
+    const uint32_t wg_lbo = (L0 ? (p.nseg == 0 ? 0u : 2u) : (p.nseg == 2 ? 2u : 0u)) * kATileBytes;
 
     if (warp == kProdWarp) {
         // ===================== producer =====================
+        TC_PROF_DECL
         if (lane == 0) {
             uint32_t wc = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int tile = blockIdx.x + i * gridDim.x;
                 if (p.nseg > 0) {
-                    if (i > 0) mbar_wait_raw(&tail->a_empty, (uint32_t)(i - 1) & 1);
+                    if (i > 0) mbar_wait_p(&tail->a_empty, (uint32_t)(i - 1) & 1, 1);
                     mbar_arrive_expect_tx(&tail->a_full, (uint32_t)(p.nseg * PLANES * kATileBytes));
                     for (int s = 0; s < p.nseg; ++s)
                         for (int pl = 0; pl < PLANES; ++pl)
                             tma_load_3d(a_sm + (size_t)(s * 2 + pl) * kATileBytes, &p.amap[s], 0, tile * kTileM, p.aslice[s] + pl,
                                         &tail->a_full);
+                    // the A planes are single-buffered (they stay resident until the tile's last weight-gradient MMA): pull
+                    // the NEXT tile's planes into L2 now so that the exposed part of their load is an L2 hit, not HBM latency
+                    if (i + 1 < my_tiles) {
+                        for (int s = 0; s < p.nseg; ++s)
+                            for (int pl = 0; pl < PLANES; ++pl)
+                                tma_prefetch_3d(&p.amap[s], 0, (tile + (int)gridDim.x) * kTileM, p.aslice[s] + pl);
+                        // ... and the compute warps' per-row inputs (a tile is one contiguous 32 KB run in every workspace):
+                        // their one-chunk-ahead register prefetch then costs an L2 hit, not a DRAM round trip
+                        const int64_t o = (int64_t)(tile + (int)gridDim.x) * kTileM * kHid;
+                        constexpr uint32_t kB = kTileM * kHid * 4;
+                        if (p.c_prev) prefetch_l2(p.c_prev + o, kB);
+                        if (p.dh_in) prefetch_l2(p.dh_in + o, kB);
+                        if (!p.first) {
+                            prefetch_l2(p.dh_rec + o, kB);
+                            prefetch_l2(p.dc + o, kB);
+                        }
+                    }
                     for (int c = 0; c < 4; ++c, ++wc) {
                         const int stg = wc % kBWStages;
                         const uint32_t ph = (wc / kBWStages) & 1;
-                        mbar_wait_raw(&tail->w_empty[stg], ph ^ 1);
+                        mbar_wait_p(&tail->w_empty[stg], ph ^ 1, 0);
                         mbar_arrive_expect_tx(&tail->w_full[stg], (uint32_t)(p.nseg * PLANES * kBWChunkTile));
                         for (int s = 0; s < p.nseg; ++s)
                             for (int pl = 0; pl < PLANES; ++pl)
@@ -486,40 +561,54 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 }
             }
         }
+        TC_PROF_FLUSH(5, lane == 0)
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
+        TC_PROF_DECL
+        // One thread issues ~240 MMAs per tile: everything that does not change is hoisted into 64-bit descriptor
+        // constants, and a k-step is a single add on the descriptor's address field (the encoded address is bytes >> 4;
+        // all operands live below 256 KB, so the 14-bit field cannot carry).
         constexpr uint32_t idesc_rc = idesc_bf16(kTileM, 64);              // recompute: A K-major, B K-major, N = 64
         constexpr uint32_t idesc_wg = idesc_bf16(kTileM, 64, 1, 1);        // weight gradient: both MN-major, M = kd (128), N = 64
         const uint32_t idesc_dg = idesc_bf16(kTileM, 64 * (p.nseg > 0 ? p.nseg : 1), 0, 1);   // data gradient: B MN-major, N = 64 * nseg
         const uint32_t a_u = smem_u32(a_sm), w_u = smem_u32(w_sm), da_u = smem_u32(da_sm);
+        constexpr uint64_t kStepK = 2;                                     // K-major: 16 bf16 = 32 bytes
+        constexpr uint64_t kStepMN = 2048 >> 4;                            // MN-major: 16 rows of 128 bytes
+        constexpr uint64_t kTileEnc = kATileBytes >> 4, kChunkEnc = kBWChunkTile >> 4, kStageEnc = kBWStageBytes >> 4;
+        const uint64_t rc_a = desc16_k(a_u);                               // + (s*2 + plane) * kTileEnc
+        const uint64_t rc_b = desc16_k(w_u);                               // + stage * kStageEnc + (s*2 + plane) * kChunkEnc
+        const uint64_t wg_a = desc16_mn(a_u + wg_a0 * kATileBytes, wg_lbo);   // hi planes; lo: + kTileEnc
+        const uint64_t wg_b = desc16_mn(da_u, kATileBytes);                // dA hi; lo: + kTileEnc
+        const uint64_t dg_a = desc16_k(da_u);                              // dA hi; lo: + kTileEnc
+        const uint64_t dg_b = desc16_mn(w_u, 2 * kBWChunkTile);            // + stage * kStageEnc (+ kChunkEnc for the lo plane)
+        const uint32_t t_rc = tmem_base + kRcCol, t_wg = tmem_base + kWgCol, t_dg = tmem_base + kDgCol;
+        const int nseg = p.nseg;
         uint32_t wc_r = 0;          // weight-chunk counter of the recompute front
         uint32_t rc = 0;            // recompute-buffer counter
-        auto issue_R = [&](int c) {
-            (void)c;
+        auto issue_R = [&]() {
             const int stg = wc_r % kBWStages;
             const uint32_t ph = (wc_r / kBWStages) & 1;
             const int b = rc & 1;
             const uint32_t bph = (rc >> 1) & 1;
-            mbar_wait_raw(&tail->w_full[stg], ph);
-            mbar_wait_raw(&tail->r_empty[b], bph ^ 1);
+            mbar_wait_p(&tail->w_full[stg], ph, 0);
+            mbar_wait_p(&tail->r_empty[b], bph ^ 1, 2);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t d = tmem_base + kRcCol + (uint32_t)b * 64;
-                const uint32_t ws = w_u + (uint32_t)stg * kBWStageBytes;
-                bool first = true;
-                for (int s = 0; s < p.nseg; ++s) {
-                    const uint64_t a_hi = desc16_k(a_u + (uint32_t)(s * 2) * kATileBytes);
-                    const uint64_t a_lo = desc16_k(a_u + (uint32_t)(s * 2 + 1) * kATileBytes);
-                    const uint64_t b_hi = desc16_k(ws + (uint32_t)(s * 2) * kBWChunkTile);
-                    const uint64_t b_lo = desc16_k(ws + (uint32_t)(s * 2 + 1) * kBWChunkTile);
+                const uint32_t d = t_rc + (uint32_t)b * 64;
+                const uint64_t bs = rc_b + (uint64_t)stg * kStageEnc;
 #pragma unroll
-                    for (int pass = 0; pass < (PLANES == 2 ? 3 : 1); ++pass) {
-                        const uint64_t da = (pass == 1) ? a_lo : a_hi;
-                        const uint64_t db = (pass == 2) ? b_lo : b_hi;
+                for (int s = 0; s < 2; ++s) {
+                    if (s < nseg) {
+                        const uint64_t a_hi = rc_a + (uint64_t)(s * 2) * kTileEnc, a_lo = a_hi + kTileEnc;
+                        const uint64_t b_hi = bs + (uint64_t)(s * 2) * kChunkEnc, b_lo = b_hi + kChunkEnc;
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            mma_bf16(d, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), idesc_rc, first ? 0u : 1u);
-                            first = false;
+                        for (int kk = 0; kk < 4; ++kk)
+                            mma_bf16(d, a_hi + kk * kStepK, b_hi + kk * kStepK, idesc_rc, (s > 0 || kk > 0) ? 1u : 0u);
+                        if (PLANES == 2) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) mma_bf16(d, a_lo + kk * kStepK, b_hi + kk * kStepK, idesc_rc, 1u);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) mma_bf16(d, a_hi + kk * kStepK, b_lo + kk * kStepK, idesc_rc, 1u);
                         }
                     }
                 }
@@ -532,59 +621,67 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         uint32_t wc_d = 0;          // weight-chunk counter of the data-gradient front
         uint32_t dcount = 0;        // dA chunks consumed
         for (int i = 0; i < my_tiles; ++i) {
-            if (p.nseg > 0) {
-                mbar_wait_raw(&tail->a_full, (uint32_t)i & 1);
+            if (nseg > 0) {
+                mbar_wait_p(&tail->a_full, (uint32_t)i & 1, 3);
                 tc_fence_after();
-                issue_R(0);
-                issue_R(1);
+                issue_R();
+                issue_R();
             }
             for (int c = 0; c < 4; ++c, ++dcount) {
-                mbar_wait_raw(&tail->d_full, dcount & 1);
-                if (c == 0 && p.nseg > 0 && i > 0) mbar_wait_raw(&tail->g_empty, (uint32_t)(i - 1) & 1);
+                mbar_wait_p(&tail->d_full, dcount & 1, 1);
+                if (c == 0 && nseg > 0 && i > 0) mbar_wait_p(&tail->g_empty, (uint32_t)(i - 1) & 1, 2);
                 tc_fence_after();
                 if (lane == 0) {
                     // ---- weight gradient: dWp[:, chunk c] += A'^T . dA_c   (M = kd 128, N = 64, K = 128 rows) ----
-                    const uint32_t d_wg = tmem_base + kWgCol + (uint32_t)c * 64;
+                    const uint32_t d_wg = t_wg + (uint32_t)c * 64;
+                    {
+                        const uint32_t acc0 = (i > 0) ? 1u : 0u;
+                        mma_bf16(d_wg, wg_a, wg_b, idesc_wg, acc0);
 #pragma unroll
-                    for (int pass = 0; pass < (PLANES == 2 ? 3 : 1); ++pass) {
-                        const uint32_t a_t = a_u + (wg_a0 + (pass == 1 ? 1u : 0u)) * kATileBytes;
-                        const uint32_t b_t = da_u + (pass == 2 ? (uint32_t)kATileBytes : 0u);
+                        for (int ks = 1; ks < 8; ++ks) mma_bf16(d_wg, wg_a + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, 1u);
+                        if (PLANES == 2) {
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_bf16(d_wg, desc16_mn(a_t + ks * 2048, wg_lbo), desc16_mn(b_t + ks * 2048, kATileBytes), idesc_wg,
-                                     (i > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+                            for (int ks = 0; ks < 8; ++ks)
+                                mma_bf16(d_wg, wg_a + kTileEnc + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, 1u);
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks)
+                                mma_bf16(d_wg, wg_a + ks * kStepMN, wg_b + kTileEnc + ks * kStepMN, idesc_wg, 1u);
+                        }
                     }
-                    if (c == 3 && p.nseg > 0) mma_commit(&tail->a_empty);          // A planes may be refilled
+                    if (c == 3 && nseg > 0) mma_commit(&tail->a_empty);            // A planes may be refilled
                     // ---- data gradient: [dx_below | dh_prev] += dA_c . Wp[:, chunk c]^T   (N = 64 * nseg, K = 64) ----
-                    if (p.nseg > 0) {
+                    if (nseg > 0) {
                         const int stg = wc_d % kBWStages;
-                        const uint32_t ws = w_u + (uint32_t)stg * kBWStageBytes;
-                        const uint32_t d_dg = tmem_base + kDgCol;
+                        const uint64_t bs = dg_b + (uint64_t)stg * kStageEnc;
 #pragma unroll
-                        for (int pass = 0; pass < (PLANES == 2 ? 3 : 1); ++pass) {
-                            const uint64_t da = desc16_k(da_u + (pass == 1 ? (uint32_t)kATileBytes : 0u));
-                            const uint32_t b_t = ws + (pass == 2 ? (uint32_t)kBWChunkTile : 0u);
+                        for (int kk = 0; kk < 4; ++kk)
+                            mma_bf16(t_dg, dg_a + kk * kStepK, bs + kk * kStepMN, idesc_dg, (c > 0 || kk > 0) ? 1u : 0u);
+                        if (PLANES == 2) {
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
-                                mma_bf16(d_dg, da + (uint64_t)(2 * kk), desc16_mn(b_t + kk * 2048, 2 * kBWChunkTile), idesc_dg,
-                                         (c > 0 || pass > 0 || kk > 0) ? 1u : 0u);
+                                mma_bf16(t_dg, dg_a + kTileEnc + kk * kStepK, bs + kk * kStepMN, idesc_dg, 1u);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                mma_bf16(t_dg, dg_a + kk * kStepK, bs + kChunkEnc + kk * kStepMN, idesc_dg, 1u);
                         }
                         mma_commit(&tail->w_empty[stg]);
                     }
                     mma_commit(&tail->d_empty);
-                    if (c == 3 && p.nseg > 0) mma_commit(&tail->g_full);
+                    if (c == 3 && nseg > 0) mma_commit(&tail->g_full);
                 }
                 __syncwarp();
-                if (p.nseg > 0) {
+                if (nseg > 0) {
                     ++wc_d;
-                    if (c + 2 < 4) issue_R(c + 2);
+                    if (c + 2 < 4) issue_R();
                 }
             }
         }
         if (lane == 0) mma_commit(&tail->done);
         __syncwarp();
+        TC_PROF_FLUSH(4, lane == 0)
     } else {
         // ===================== compute warps =====================
+        TC_PROF_DECL
         // TMEM lane quadrant q = warp & 3 (row 32q + lane of the tile), part = warp >> 2: units 4*part .. +3 of every chunk
         const int q = warp & 3, part = warp >> 2;
         const int ctid = tid;
@@ -593,12 +690,14 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         uint32_t dcount = 0, rcount = 0;
         // raw inputs of one chunk: c_prev, dh_in, dh_rec, dc of this thread's 4 units
         struct Raw { float4 cp, dhi, dhr, dcv; };
+        // tile-blocked workspaces: element (tile, row, unit) at tile*8192 + (unit/8)*1024 + row*8 + unit%8
+        const int64_t thr_off = (int64_t)(q * 32 + lane) * 8 + (part >> 1) * 1024 + (part & 1) * 4;
         auto load_raw = [&](int tile, int c, Raw& rw) {
             const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             rw.cp = rw.dhi = rw.dhr = rw.dcv = z;
             if (tile < p.n_tiles && r < p.rows) {
-                const int64_t o = ws_off(r, 16 * c + 4 * part);
+                const int64_t o = (int64_t)tile * (kTileM * kHid) + c * 2048 + thr_off;
                 if (p.c_prev) rw.cp = *reinterpret_cast<const float4*>(p.c_prev + o);
                 if (p.dh_in) rw.dhi = *reinterpret_cast<const float4*>(p.dh_in + o);
                 if (!p.first) {
@@ -610,7 +709,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         auto drain = [&](int i_prev) {          // [dx_below | dh_prev] of tile i_prev: TMEM -> tile-blocked workspaces
             const int tile = blockIdx.x + i_prev * gridDim.x;
             const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
-            mbar_wait_raw(&tail->g_full, (uint32_t)i_prev & 1);
+            mbar_wait(&tail->g_full, (uint32_t)i_prev & 1, 2);
             tc_fence_after();
             const int ncols = 64 * p.nseg;
             if (part * 32 < ncols) {
@@ -619,7 +718,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 tmem_ld_wait();
                 const int col = part * 32;
                 // layers > 0: columns [0,64) = dx_below, [64,128) = dh_prev; layer 0: [0,64) = dh_prev
-                const bool is_dx = !p.layer0 && col < 64;
+                const bool is_dx = !L0 && col < 64;
                 float* base = is_dx ? p.dx_out : p.dh_rec;
                 const int unit0 = col & 63;
                 if (r < p.rows && base != nullptr && (is_dx || p.store_dh)) {
@@ -629,7 +728,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tail->g_empty);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tail->g_empty);
         };
         Raw cur, nxt;
         load_raw((int)blockIdx.x, 0, nxt);
@@ -637,7 +737,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             const int tile = blockIdx.x + i * gridDim.x;
             const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
             const bool valid = r < p.rows;
-            if (p.layer0) {
+            if (L0) {
                 float sv = 0.f;
                 if (valid) sv = p.sg[(r % p.b_inner) * p.t_len + p.t];
 #pragma unroll
@@ -650,8 +750,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             if (i > 0 && p.nseg > 0) drain(i - 1);
             if (have_aux && part == 0) {
                 // auxiliary weight-gradient operand: tile 2 (hi) / tile 3 (lo), row = this thread's row, columns 0..C-1 = x*s
-                if (i > 0 && p.nseg > 0) mbar_wait_raw(&tail->a_empty, (uint32_t)(i - 1) & 1);
-                else if (i > 0) mbar_wait_raw(&tail->d_empty, (dcount - 1) & 1);      // no A planes: the last W_3 read the tile
+                if (i > 0 && p.nseg > 0) mbar_wait(&tail->a_empty, (uint32_t)(i - 1) & 1, 3);
+                else if (i > 0) mbar_wait(&tail->d_empty, (dcount - 1) & 1, 0);      // no A planes: the last W_3 read the tile
                 uint32_t hi[2], lo[2];
                 split_bf16x2(xs[0], xs[1], hi[0], lo[0]);
                 split_bf16x2(xs[2], xs[3], hi[1], lo[1]);
@@ -667,12 +767,13 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 uint32_t v[16];
                 if (p.nseg > 0) {
                     const int b = rcount & 1;
-                    mbar_wait_raw(&tail->r_full[b], (rcount >> 1) & 1);
+                    mbar_wait(&tail->r_full[b], (rcount >> 1) & 1, 1);
                     tc_fence_after();
                     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kRcCol + (uint32_t)b * 64 + (uint32_t)part * 16, v);
                     tmem_ld_wait();
                     tc_fence_before();
-                    mbar_arrive(&tail->r_empty[b]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tail->r_empty[b]);
                     ++rcount;
                 } else {
 #pragma unroll
@@ -692,7 +793,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     float pf = __uint_as_float(v[4 * u + 1]) + bv.y;
                     float pg = __uint_as_float(v[4 * u + 2]) + bv.z;
                     float po = __uint_as_float(v[4 * u + 3]) + bv.w;
-                    if (p.layer0) {
+                    if (L0) {
 #pragma unroll
                         for (int cc = 0; cc < kMaxC; ++cc)
                             if (cc < p.c_in) {
@@ -701,9 +802,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                                 pg = fmaf(xs[cc], wv.z, pg); po = fmaf(xs[cc], wv.w, po);
                             }
                     }
-                    const float gi = sigmoidf_(pi), gf = sigmoidf_(pf), gg = tanhf_(pg), go = sigmoidf_(po);
-                    const float ct = fmaf(gf, cp[u], gi * gg);
-                    const float tc_ = tanhf_(ct);
+                    float gi, gf, gg, go, tc_;
+                    lstm_cell_gates8(pi, pf, pg, po, cp[u], gi, gf, gg, go, tc_);
                     const float dh = valid ? (dhr[u] + dhi[u]) : 0.f;
                     const float dcv = valid ? fmaf(dh * go, 1.f - tc_ * tc_, dci[u]) : 0.f;
                     da[4 * u + 0] = dcv * gg * gi * (1.f - gi);
@@ -711,7 +811,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     da[4 * u + 2] = dcv * gi * (1.f - gg * gg);
                     da[4 * u + 3] = dh * tc_ * go * (1.f - go);
                     dcn[u] = dcv * gf;
-                    if (p.layer0) {
+                    if (L0) {
 #pragma unroll
                         for (int cc = 0; cc < kMaxC; ++cc)
                             if (cc < p.c_in) {
@@ -727,7 +827,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     if (PLANES == 2) split_bf16x2(da[2 * j], da[2 * j + 1], hi[j], lo[j]);
                     else hi[j] = pack_bf16x2(da[2 * j], da[2 * j + 1]);
                 }
-                if (dcount > 0) mbar_wait_raw(&tail->d_empty, (dcount - 1) & 1);     // W_{c-1}, D_{c-1} have read the dA tile
+                if (dcount > 0) mbar_wait(&tail->d_empty, (dcount - 1) & 1, 0);     // W_{c-1}, D_{c-1} have read the dA tile
                 {
                     const uint32_t row = (uint32_t)(q * 32 + lane);
                     const uint32_t o0 = row * 128u + ((((uint32_t)(2 * part)) ^ (row & 7u)) << 4);
@@ -740,8 +840,11 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     }
                 }
                 fence_proxy_async_smem();
-                mbar_arrive(&tail->d_full);
-                if (valid) *reinterpret_cast<float4*>(p.dc + ws_off(r, unit0)) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tail->d_full);
+                if (valid)
+                    *reinterpret_cast<float4*>(p.dc + (int64_t)tile * (kTileM * kHid) + c * 2048 + thr_off) =
+                        make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
                 // bias gradient: column sums over the warp's 32 rows by a halving butterfly (16 shuffles), then one
                 // shared-memory atomic per column from the even lanes
                 {
@@ -777,7 +880,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     }
                 }
             }
-            if (p.layer0 && valid) {
+            if (L0 && valid) {
                 // gate adjoint: d s[b, t] += sum_c dxmod[r, c] * xo[r, t, c]   (STMGCN.py:44)
                 float contrib = 0.f;
 #pragma unroll
@@ -788,6 +891,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             }
         }
         if (my_tiles > 0 && p.nseg > 0) drain(my_tiles - 1);
+        TC_PROF_FLUSH(3, tid == 0)
         // ---- weight-gradient accumulator -> this CTA's scratch slice (register layout: [part][piece][vec][row m][4]) ----
         if (my_tiles > 0) {
             mbar_wait_raw(&tail->done, 0);
@@ -823,7 +927,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     tc_fence_after();
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
     for (int i = tid; i < kGateCols; i += kBThreads) atomicAdd(&p.dbp[i], tail->s_db[i]);
-    if (p.layer0 && p.b_inner <= kBSgMax)
+    if (L0 && p.b_inner <= kBSgMax)
         for (int i = tid; i < (int)p.b_inner; i += kBThreads) atomicAdd(&p.d_s[(int64_t)i * p.t_len + p.t], tail->s_ds[i]);
 }
 
@@ -1015,7 +1119,8 @@ extern "C" int32_t stmgcn_lstm16_step_bwd(int32_t t, int32_t t_len, int32_t n_la
     cudaStream_t st = (cudaStream_t)stream;
     const int n_tiles = (int)ceil_div(rows, kTileM);
     const int64_t cslice = (int64_t)n_tiles * kTileM * kHid;
-    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_bwd_kernel<2> : (const void*)lstm16_bwd_kernel<1>, kBSmem)) return rc;
+    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_bwd_kernel<2, true> : (const void*)lstm16_bwd_kernel<1, true>, kBSmem)) return rc;
+    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_bwd_kernel<2, false> : (const void*)lstm16_bwd_kernel<1, false>, kBSmem)) return rc;
     CUtensorMap hp_map, h0_map;
     STMGCN_REQUIRE(make_plane_map(&hp_map, hp, rows, (int64_t)n_layers * t_len * planes), STMGCN_ERR_STATE,
                    "lstm16_step_bwd: cuTensorMapEncodeTiled failed (hp)");
@@ -1073,8 +1178,13 @@ extern "C" int32_t stmgcn_lstm16_step_bwd(int32_t t, int32_t t_len, int32_t n_la
         }
         p.rows = rows;
         p.n_tiles = n_tiles;
-        if (planes == 2) lstm16_bwd_kernel<2><<<grid, kBThreads, kBSmem, st>>>(p);
-        else lstm16_bwd_kernel<1><<<grid, kBThreads, kBSmem, st>>>(p);
+        if (planes == 2) {
+            if (l == 0) lstm16_bwd_kernel<2, true><<<grid, kBThreads, kBSmem, st>>>(p);
+            else lstm16_bwd_kernel<2, false><<<grid, kBThreads, kBSmem, st>>>(p);
+        } else {
+            if (l == 0) lstm16_bwd_kernel<1, true><<<grid, kBThreads, kBSmem, st>>>(p);
+            else lstm16_bwd_kernel<1, false><<<grid, kBThreads, kBSmem, st>>>(p);
+        }
         count_launch();
         if (int32_t rc = check_launch("lstm16_bwd")) return rc;
     }
@@ -1091,3 +1201,16 @@ extern "C" int32_t stmgcn_lstm16_wgrad_reduce(int32_t layer, int32_t c_in, int32
     count_launch();
     return check_launch("lstm16_wgrad_reduce");
 }
+
+#ifdef STMGCN_TC_PROFILE
+// per-role wait accounting of THIS translation unit's kernels (see tc_common.cuh); instrumented builds only
+extern "C" int32_t stmgcn_dbg_tc_prof16(unsigned long long* host_out, int32_t reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_out, stmgcn::tc::g_tc_prof, sizeof(unsigned long long) * 64);
+    if (reset) {
+        unsigned long long z[64] = {0};
+        cudaMemcpyToSymbol(stmgcn::tc::g_tc_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif

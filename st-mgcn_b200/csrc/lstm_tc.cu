@@ -107,7 +107,7 @@ __global__ void __launch_bounds__((FwdCfg<A_TMA>::kThreads), 1) lstm_cell_tc_ker
     constexpr int kFwdLoaders = FwdCfg<A_TMA>::kLoaders;
     constexpr int kFwdThreads = FwdCfg<A_TMA>::kThreads;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the __shared__ address space (LDS/STS, not generic LD/ST)
     uint8_t* staging = smem + (size_t)kFwdStages * kFwdStageBytes;
     FwdTail* tail = (FwdTail*)(staging + (size_t)kFwdEpiWarps * kStagingBytes);
     Barriers* bar = &tail->bar;
@@ -405,7 +405,7 @@ static_assert(kNsSmem <= 232448, "N-split forward kernel exceeds the 227 KB shar
 
 __global__ void __launch_bounds__(kNsThreads, 1) lstm_cell_nsplit_kernel(const __grid_constant__ CellParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the __shared__ address space (LDS/STS, not generic LD/ST)
     uint8_t* bres = smem;                                          // resident weight half: nkb x [hi 16 KB | lo 16 KB]
     uint8_t* stages = bres + (size_t)kNsMaxKb * kNsBkb;
     uint8_t* staging = stages + (size_t)kNsStages * kNsAStage;
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__((BwdCfg<N, TMA>::kThreads), 1) lstm_bwd_tc_ker
     constexpr int kBwdStages = Cfg::kStages;
     constexpr int kBwdThreads = Cfg::kThreads;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the __shared__ address space (LDS/STS, not generic LD/ST)
     using BwdTail = typename Cfg::BwdTail;
     uint8_t* raw = smem + (size_t)kBwdStages * Cfg::kStageBytes;
     BwdTail* tail = (BwdTail*)(raw + Cfg::kRawBytes);
@@ -1090,7 +1090,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
     constexpr int kWgBBytes = Cfg::kBBytes;
     constexpr int kWgStageBytes = Cfg::kStageBytes;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the __shared__ address space (LDS/STS, not generic LD/ST)
     WgTail* tail = (WgTail*)(smem + (size_t)kWgStages * kWgStageBytes);
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -1261,7 +1261,7 @@ static_assert(kWtSmem <= 232448, "wgrad TMA kernel exceeds the 227 KB shared-mem
 
 __global__ void __launch_bounds__(kWtThreads, 1) lstm_wgrad_tma_kernel(const __grid_constant__ WgParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the __shared__ address space (LDS/STS, not generic LD/ST)
     uint8_t* raw = smem + (size_t)kWtStages * kWtStageBytes;
     WtTail* tail = (WtTail*)(raw + (size_t)kWtSlots * kWtRawBytes);
     const int tid = threadIdx.x;

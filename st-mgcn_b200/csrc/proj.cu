@@ -173,12 +173,17 @@ extern "C" {
 
 int32_t stmgcn_proj_pack_tc(const float* w, int32_t ks, float* img_fwd, float* img_bwd, void* stream) {
     STMGCN_REQUIRE(w && img_fwd, STMGCN_ERR_ARG, "proj_pack_tc: null pointer");
-    STMGCN_REQUIRE(ks >= 1 && ks <= 4, STMGCN_ERR_SHAPE, "proj_pack_tc: ks=%d (tensor-core path supports 1..4 supports)", ks);
+    STMGCN_REQUIRE(ks >= 1 && ks <= 8, STMGCN_ERR_SHAPE, "proj_pack_tc: ks=%d (tensor-core path supports 1..8 supports)", ks);
     cudaStream_t st = (cudaStream_t)stream;
     // forward operand B[n = out col][k = ks*64 index] = W[k][n]
     if (int32_t rc = launch_pack_image(w, 64, ks * 64, 1, 64, img_fwd, 64, st)) return rc;
-    // backward operand B[n = k*64+i][k' = out col] = W[n][k'], tile padded to 256 rows (caller zero-fills img_bwd)
-    if (img_bwd) return launch_pack_image(w, ks * 64, 64, 64, 1, img_bwd, 256, st);
+    // backward operand B[n = k*64+i][k' = out col] = W[n][k'], one 256-row image per group of 4 supports (caller
+    // zero-fills img_bwd: rows beyond the last support stay zero)
+    if (img_bwd) {
+        const int k0 = ks < 4 ? ks : 4;
+        if (int32_t rc = launch_pack_image(w, k0 * 64, 64, 64, 1, img_bwd, 256, st)) return rc;
+        if (ks > 4) return launch_pack_image(w + (int64_t)256 * 64, (ks - 4) * 64, 64, 64, 1, img_bwd + 2 * 2 * 256 * 32, 256, st);
+    }
     return 0;
 }
 
@@ -234,7 +239,13 @@ int32_t stmgcn_proj_bwd(const float* s, int64_t stride_k, int32_t ks, int64_t ro
     if (wimg_t && u && d_out && proj_tc_applicable(ks, p, q, s, out, d_out) && aligned16(dz_work) && aligned16(u) &&
         stride_k % 4 == 0 && stride_u % 4 == 0) {
         // tcgen05 path: dZ + bias gradient + U in one kernel, then dW per 128-row block of W (proj_tc.cu, lstm_tc.cu)
-        if (int32_t rc = launch_proj_bwd_tc(d_out, out, act, rows, ks, wimg_t, dz_work, dbias, u, stride_u, st)) return rc;
+        // U has 64*ks columns; one launch produces up to 256 of them (supports 0..3), a second one the rest (it re-forms
+        // dZ in its loader but neither stores it nor accumulates the bias gradient again)
+        if (int32_t rc = launch_proj_bwd_tc(d_out, out, act, rows, ks < 4 ? ks : 4, wimg_t, dz_work, dbias, u, stride_u, st)) return rc;
+        if (ks > 4)
+            if (int32_t rc = launch_proj_bwd_tc(d_out, out, act, rows, ks - 4, wimg_t + 2 * 2 * 256 * 32, nullptr, nullptr,
+                                                u + 4 * stride_u, stride_u, st))
+                return rc;
         for (int k0 = 0; k0 < ks; k0 += 2) {
             const bool two = k0 + 1 < ks;
             const float* s0 = two ? s + (int64_t)k0 * stride_k : nullptr;

@@ -41,7 +41,7 @@ struct PParams {
     const float* d_out;          // (rows, 64) or nullptr
     const float* out_act;        // (rows, 64) forward output (mask source)
     int act;
-    float* dz_out;               // (rows, 64)
+    float* dz_out;               // (rows, 64) or nullptr (second pass of a > 4-support backward: dZ is already stored)
     float* dbias;                // (64) += or nullptr
     const float* wimg;
     const float* bias;           // forward epilogue
@@ -57,7 +57,7 @@ template <int N, bool DZ>
 __global__ void __launch_bounds__(PCfg<N>::kThreads, 1) proj_rows_tc_kernel(const __grid_constant__ PParams p) {
     using Cfg = PCfg<N>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the __shared__ address space (LDS/STS, not generic LD/ST)
     PTail* tail = (PTail*)(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
     Barriers* bar = &tail->bar;
     const int tid = threadIdx.x;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(PCfg<N>::kThreads, 1) proj_rows_tc_kernel(cons
 #pragma unroll
                 for (int i = 0; i < kPer; ++i) {
                     const int64_t r = (int64_t)tile * kTileM + rsub + (kGT / 8) * i;
-                    if (r < p.rows) *reinterpret_cast<float4*>(p.dz_out + r * 64 + koff) = v[i];
+                    if (r < p.rows && p.dz_out != nullptr) *reinterpret_cast<float4*>(p.dz_out + r * 64 + koff) = v[i];
                 }
             }
         }
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(PCfg<N>::kThreads, 1) proj_rows_tc_kernel(cons
 namespace stmgcn {
 
 bool proj_tc_applicable(int ks, int p, int q, const void* a, const void* b, const void* c) {
-    return p == 64 && q == 64 && ks >= 1 && ks <= 4 && aligned16(a) && aligned16(b) && (!c || aligned16(c));
+    return p == 64 && q == 64 && ks >= 1 && ks <= 8 && aligned16(a) && aligned16(b) && (!c || aligned16(c));
 }
 
 // forward: out = act(sum_k S_k W_k + bias); wimg = image of B[n][k] = W[k][n] (2*ks k-blocks of [hi|lo] [64][32])

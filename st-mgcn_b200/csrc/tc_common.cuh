@@ -59,6 +59,17 @@ __device__ __forceinline__ void mbar_wait_raw(uint64_t* bar, uint32_t parity) {
     }
     __trap();
 }
+// Polite wait for the single-thread roles (TMA producer, MMA issuer): a spinning warp competes for issue slots with the
+// warps doing the arithmetic on the same SM sub-partition (ncu: a quarter of all executed instructions were try_wait /
+// branch pairs), so back off ~40 ns between polls; the bound is the same ~20 s.
+__device__ __forceinline__ void mbar_wait_polite(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    for (uint32_t it = 0; it < (1u << 28); ++it) {
+        __nanosleep(40);
+        if (mbar_try_wait(bar, parity)) return;
+    }
+    __trap();
+}
 // Optional wait-time accounting (built with -DSTMGCN_TC_PROFILE): cycles each role spends blocked on each barrier
 // class, summed per launch into g_tc_prof[slot]; slot = role*4 + barrier class.  Read with stmgcn_dbg_tc_prof().
 #ifdef STMGCN_TC_PROFILE
@@ -77,10 +88,12 @@ struct WaitProf {
 #define TC_PROF_DECL WaitProf _wp;
 #define TC_PROF_FLUSH(role, leader) _wp.flush(role, leader);
 #define mbar_wait(bar, parity, cls) do { long long _t0 = clock64(); mbar_wait_raw(bar, parity); _wp.acc[cls] += clock64() - _t0; } while (0)
+#define mbar_wait_p(bar, parity, cls) do { long long _t0 = clock64(); mbar_wait_polite(bar, parity); _wp.acc[cls] += clock64() - _t0; } while (0)
 #else
 #define TC_PROF_DECL
 #define TC_PROF_FLUSH(role, leader)
 #define mbar_wait(bar, parity, cls) mbar_wait_raw(bar, parity)
+#define mbar_wait_p(bar, parity, cls) mbar_wait_polite(bar, parity)
 #endif
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies read smem through it)

@@ -17,8 +17,9 @@ ROOT = os.path.dirname(PKG_DIR)                      # st-mgcn_b200/
 REPO = os.path.dirname(ROOT)
 CSRC = os.path.join(ROOT, "csrc")
 LIB_DIR = os.path.join(ROOT, "lib")
-OBJ_DIR = os.path.join(ROOT, "build")
-LIB_PATH = os.path.join(LIB_DIR, "libstmgcn_b200.so")
+_PROF = bool(os.environ.get("STMGCN_TC_PROFILE"))       # instrumented build (per-role wait accounting): separate objects and .so
+OBJ_DIR = os.path.join(ROOT, "build_prof" if _PROF else "build")
+LIB_PATH = os.path.join(LIB_DIR, "libstmgcn_b200_prof.so" if _PROF else "libstmgcn_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # the long form: `-arch=sm_100a` drops the `a` features

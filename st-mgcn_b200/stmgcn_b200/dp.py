@@ -29,13 +29,46 @@ class GradBucket:
             p.grad = self.flat[off:off + p.numel()].view_as(p)      # autograd accumulates in place
             off += p.numel()
 
+        self._offsets = []
+        off = 0
+        for p in self.params:
+            self._offsets.append(off)
+            off += p.numel()
+
     def zero_(self) -> None:
         self.flat.zero_()
 
+    def rebind_(self) -> int:
+        """Make sure every ``p.grad`` still IS its view into the flat buffer.  ``optimizer.zero_grad()`` defaults to
+        ``set_to_none=True`` (and so does ``Model_Trainer.py:40``'s call): it drops the views, autograd then allocates fresh
+        ``.grad`` tensors and an all-reduce of the flat buffer would silently average zeros.  Gradients found outside the
+        buffer are copied in and re-aliased.  Returns the number of parameters that had to be re-bound."""
+        fixed = 0
+        base = self.flat.data_ptr()
+        esz = self.flat.element_size()
+        for p, off in zip(self.params, self._offsets):
+            view = self.flat[off:off + p.numel()].view_as(p)
+            g = p.grad
+            if g is None:
+                view.zero_()
+                p.grad = view
+                fixed += 1
+            elif g.data_ptr() != base + off * esz or not g.is_contiguous():
+                view.copy_(g)
+                p.grad = view
+                fixed += 1
+        return fixed
+
     def all_reduce_mean_(self, group=None) -> None:
+        """ONE collective over the flat bucket.  NCCL averages inside the collective (``ReduceOp.AVG``): the step has a
+        single post-backward kernel; gloo (CPU tests) has no AVG, so SUM + scale."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.mul_(1.0 / dist.get_world_size(group))
+            self.rebind_()
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.mul_(1.0 / dist.get_world_size(group))
 
 
 def init_from_env(backend: Optional[str] = None):

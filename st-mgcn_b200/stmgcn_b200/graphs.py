@@ -52,6 +52,16 @@ class GraphedStep:
     def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Copy the batch into the static buffers (host or device source) and replay. Returns the loss tensor
         (static buffer: read it before the next call)."""
+        if x is not None and tuple(x.shape) != tuple(self.x.shape):
+            # a batch of another size (the reference's DataLoader yields one short last batch, Data_Container.py:122):
+            # shapes are baked into the captured graph, so this batch runs eagerly
+            self.bucket.zero_()
+            out = self.model(obs_seq=x.to(self.x.device, non_blocking=True), sta_adj_list=self.supports)
+            loss = self.criterion(out, y.to(self.y.device, non_blocking=True))
+            loss.backward()
+            if self.all_reduce:
+                self.bucket.all_reduce_mean_()
+            return loss
         if x is not None:
             self.x.copy_(x, non_blocking=True)
         if y is not None:

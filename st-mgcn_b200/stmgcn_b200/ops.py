@@ -132,10 +132,10 @@ def adjoint_stack_(sset: SupportSet, u: torch.Tensor) -> torch.Tensor:
 
 def _proj_images(w: torch.Tensor, ks: int, p: int, need_bwd: bool):
     """tcgen05 operand images of the projection weights (p = q = 64, ks <= 4), or (None, None)."""
-    if lstm_path() != "tc" or p != 64 or w.shape[1] != 64 or ks > 4:
+    if lstm_path() != "tc" or p != 64 or w.shape[1] != 64 or ks > 8:
         return None, None
     img_f = torch.empty(ks * 64 * 64 * 2, device=w.device, dtype=torch.float32)
-    img_b = torch.zeros(2 * 2 * 256 * 32, device=w.device, dtype=torch.float32) if need_bwd else None
+    img_b = torch.zeros((2 if ks > 4 else 1) * 2 * 2 * 256 * 32, device=w.device, dtype=torch.float32) if need_bwd else None
     _lib.check(L.stmgcn_proj_pack_tc(w.data_ptr(), ks, img_f.data_ptr(), _p(img_b), _stream()), "proj_pack_tc")
     return img_f, img_b
 

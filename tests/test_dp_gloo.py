@@ -48,6 +48,14 @@ def _worker(rank, world, port, out_dir):
         bucket.zero_()
         torch.nn.functional.mse_loss(model(xs), ys).backward()
         bucket.all_reduce_mean_()
+    # third pass the way the reference trainer does it (Model_Trainer.py:40-41): optimizer.zero_grad() defaults to
+    # set_to_none=True and drops the views into the bucket; all_reduce_mean_ must notice and re-bind, not average zeros
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)
+    opt.zero_grad()
+    assert all(p.grad is None for p in model.parameters())
+    torch.nn.functional.mse_loss(model(xs), ys).backward()
+    bucket.all_reduce_mean_()
+    assert all(p.grad.data_ptr() == bucket.flat.data_ptr() + o * 4 for p, o in zip(bucket.params, bucket._offsets))
     np.save(os.path.join(out_dir, f"g{rank}.npy"), bucket.flat.numpy())
     dist.barrier()
     dist.destroy_process_group()

@@ -60,6 +60,7 @@ def test_reference_main_runs_unchanged_on_the_b200_modules(tmp_path):
         sys.path[:0] = [REPO, os.path.join(REPO, "st-mgcn_b200"), REF]
         # train on one week of hourly windows (135 train -> last batch of 7, 33 validate), test on two days
         sys.argv = ["Main.py", "--device", "cuda:0", "--dates", "0101", "0107", "0108", "0109"]
+        torch.manual_seed(1234)        # Main.py sets no seed: fix the parameter init so the run is comparable (see below)
         with redirect_stdout(buf):
             runpy.run_path(os.path.join(REF, "Main.py"), run_name="__main__")
         used = {k: os.path.abspath(sys.modules[k].__file__) for k in ("GCN", "STMGCN", "Model_Trainer", "Data_Container")}
@@ -81,13 +82,17 @@ def test_reference_main_runs_unchanged_on_the_b200_modules(tmp_path):
     for metric in ("test true MSE", "test true RMSE", "test true MAE", "test true MAPE"):
         assert metric in log, log[-2000:]
     rmse = float(log.split("test true RMSE:")[1].split()[0])
-    # anchor: the unmodified reference (its own GCN/STMGCN, CPU, same script, same synthetic file) printed
-    # "test true RMSE: 2.3133" in the build container; 100 epochs of Adam are chaotic at the 1e-6 level, the
-    # converged error (dominated by the data's sigma = 2 noise) is not
-    assert np.isfinite(rmse) and abs(rmse - 2.3133) / 2.3133 < 0.05, rmse
-    # validation loss went down over the run (the model actually learns through our backward)
     drops = [float(v) for v in re.findall(r"to ([0-9.eE+-]+)\. Update model checkpoint", log)]
-    assert len(drops) >= 2 and drops[-1] < drops[0], drops
+    # anchors: the UNMODIFIED reference (its own GCN/STMGCN on the CPU, same script, same synthetic file, same
+    # torch.manual_seed(1234)) printed these validation losses for epochs 1-3 and "test true RMSE: 2.31858" in the build
+    # container.  Same seed => bit-identical init here (tests/test_abi_and_host.py), so the first epochs (15 Adam steps)
+    # must track the reference closely; 100 epochs later only the converged error is comparable.
+    ref_first, ref_rmse = [0.19774, 0.19067, 0.16364], 2.31858
+    assert len(drops) >= 3, drops
+    for got, want in zip(drops[:3], ref_first):
+        assert abs(got - want) / want < 0.02, (drops[:3], ref_first)
+    assert drops[-1] < 0.25 * drops[0], drops
+    assert np.isfinite(rmse) and abs(rmse - ref_rmse) / ref_rmse < 0.10, rmse
     ckpt = torch.load(tmp_path / "output" / "ST_MGCN_best_model.pkl", map_location="cpu")
     keys = set(ckpt["state_dict"].keys())
     assert "rnn_list.0.lstm.weight_ih_l0" in keys and "gcn_list.2.W" in keys and "fc.weight" in keys
