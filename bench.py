@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch")
+    ap.add_argument("--arith", default="auto", choices=["auto", "fp32", "bf16"],
+                    help="tensor-core arithmetic of the shared LSTM: fp32 = 3-pass bf16 hi/lo planes (fp32-grade, 1e-4 parity), "
+                         "bf16 = single pass on one bf16 plane; auto = what BASELINE.json quotes the workload in")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cuda-graph", action="store_true",
@@ -262,9 +265,9 @@ def run_reference(args, w):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(w, world, per_gpu_batch):
+def workload_config(w, world, per_gpu_batch, arith="fp32"):
     return {"workload": f"{w.name}: {w.n_regions} regions, {w.n_graphs} graphs, Chebyshev K={w.cheb_order}, "
-                        f"seq_len={w.seq_len}, batch={per_gpu_batch}/GPU x {world} GPU(s), fp32, H={w.lstm_hidden} "
+                        f"seq_len={w.seq_len}, batch={per_gpu_batch}/GPU x {world} GPU(s), {arith}, H={w.lstm_hidden} "
                         f"L={w.lstm_layers} G={w.gcn_hidden} C={w.input_dim}, graph density {w.density}",
             "global_batch": per_gpu_batch * world, "parallelism": f"dp{world}",
             "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
@@ -284,6 +287,8 @@ def run_ours(args, w):
     from stmgcn_b200 import _lib, dp, graphs, ops, synth
     from stmgcn_b200.graph import supports_from_dense
 
+    arith = args.arith if args.arith != "auto" else ("bf16" if w.dtype == "bf16" else "fp32")
+    ops.set_lstm_planes(1 if arith == "bf16" else 2)
     rank, world, local_rank = dp.init_from_env()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
@@ -555,7 +560,7 @@ def run_ours(args, w):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if ops.lstm_planes() == 2 else "bf16", "data": "synthetic",
-                "config": dict(workload_config(w, world, b), cuda_graph=use_graph,
+                "config": dict(workload_config(w, world, b, arith), cuda_graph=use_graph,
                                arithmetic=("fp32 state and accumulation; tensor-core products as 3-pass bf16 hi/lo planes "
                                            "(3xBF16, fp32-grade)" if ops.lstm_planes() == 2 else
                                            "fp32 state and accumulation; single-pass bf16 tensor-core products")),

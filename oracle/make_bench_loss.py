@@ -41,9 +41,15 @@ def reference_loss(w, batch, rank, dtype=np.float64):
     params = {k: v.detach().numpy() for k, v in model.state_dict().items()}
     x, y = synth.make_inputs(w, seed=100 + rank, batch=batch)
     orc = O.SparseOracle(params, laps, w.n_supports, dtype=dtype)
-    out = orc.forward(x.numpy())
-    diff = out - y.numpy().astype(dtype)
-    return float(np.mean(diff * diff))
+    # windows are independent (STMGCN.py:47): evaluate a few at a time to bound the oracle's memory
+    sq, cnt = 0.0, 0
+    step = max(1, min(batch, 4096 * 4 // w.n_regions))
+    for b0 in range(0, batch, step):
+        out = orc.forward(x[b0:b0 + step].numpy())
+        diff = out - y[b0:b0 + step].numpy().astype(dtype)
+        sq += float(np.sum(diff * diff))
+        cnt += diff.size
+    return sq / cnt
 
 
 def main():

@@ -52,31 +52,34 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, in
 // ---- LSTM cell with 8 MUFU operations instead of 10 ------------------------------------------------------------
 // sigmoid(v) = 1 / (1 + e^-v), tanh(v) = (1 - e^-2v) / (1 + e^-2v).  Five exponentials per cell are unavoidable (i, f, g, o,
 // tanh(c)); the five reciprocals are not: reciprocals of PRODUCTS of two (1 + e) terms serve two activations at once.
-// Arguments are clamped (sigmoid +-30, tanh +-15: the clamped values differ from the exact ones by < 1e-13) so that a
+// The exponentials are capped at e^30 (the capped activations differ from the exact ones by < 1e-13) so that a
 // product of two (1 + e^30) terms stays far below the fp32 overflow threshold.  The cell epilogue is MUFU-bound
 // (16 MUFU results per clock and SM), so this is 20 % off its critical resource.
-__device__ __forceinline__ float exp_neg_(float v) { return ex2_ftz_(-1.4426950408889634f * fminf(fmaxf(v, -30.f), 30.f)); }
-__device__ __forceinline__ float exp_neg2_(float v) { return ex2_ftz_(-2.8853900817779268f * fminf(fmaxf(v, -15.f), 15.f)); }
-// forward: pre-activations (i, f, g, o) and c_{t-1} -> c_t, h_t
-__device__ __forceinline__ void lstm_cell_fwd8(float pi, float pf, float pg, float po, float cp, float& c, float& h) {
-    const float ei = exp_neg_(pi), ef = exp_neg_(pf), eg = exp_neg2_(pg), eo = exp_neg_(po);
+// (one-sided: only a large NEGATIVE argument makes e^-v large; for large positive v the exponential underflows to 0, which is exact)
+// The kernels keep bias and W_ih PRE-SCALED by the exponent factor of their gate (kGateScale: -log2(e) for i, f, o and
+// -2 log2(e) for g), so "accumulator + bias, times -log2(e)" is ONE fma per gate: arg = fma(acc, scale, bias_scaled).
+__device__ __forceinline__ float gate_scale(int col) { return (col & 3) == 2 ? -2.8853900817779268f : -1.4426950408889634f; }
+__device__ __forceinline__ float exp_arg_(float a) { return ex2_ftz_(fminf(a, 43.28f)); }      // e^(-v) or e^(-2v), <= e^30
+// forward: exponent arguments of (i, f, g, o) and c_{t-1} -> c_t, h_t
+__device__ __forceinline__ void lstm_cell_fwd8(float ai, float af, float ag, float ao, float cp, float& c, float& h) {
+    const float ei = exp_arg_(ai), ef = exp_arg_(af), eg = exp_arg_(ag), eo = exp_arg_(ao);
     const float ig = (1.f - eg) * rcp_ftz_((1.f + ei) * (1.f + eg));          // sigmoid(pi) * tanh(pg)
     c = fmaf(rcp_ftz_(1.f + ef), cp, ig);
-    const float ec = exp_neg2_(c);
+    const float ec = exp_arg_(-2.8853900817779268f * c);
     h = (1.f - ec) * rcp_ftz_((1.f + eo) * (1.f + ec));                      // sigmoid(po) * tanh(c)
 }
 // backward recompute: all four gate activations, c_t and tanh(c_t)
-__device__ __forceinline__ void lstm_cell_gates8(float pi, float pf, float pg, float po, float cp, float& gi, float& gf,
+__device__ __forceinline__ void lstm_cell_gates8(float ai, float af, float ag, float ao, float cp, float& gi, float& gf,
                                                  float& gg, float& go, float& tc) {
-    const float ei = 1.f + exp_neg_(pi), ef = 1.f + exp_neg_(pf), eo = 1.f + exp_neg_(po);
-    const float eg = exp_neg2_(pg);
+    const float ei = 1.f + exp_arg_(ai), ef = 1.f + exp_arg_(af), eo = 1.f + exp_arg_(ao);
+    const float eg = exp_arg_(ag);
     const float r1 = rcp_ftz_(ei * (1.f + eg));
     const float r2 = rcp_ftz_(ef * eo);
     gi = r1 * (1.f + eg);
     gg = (1.f - eg) * (r1 * ei);
     gf = r2 * eo;
     go = r2 * ef;
-    const float ec = exp_neg2_(fmaf(gf, cp, gi * gg));
+    const float ec = exp_arg_(-2.8853900817779268f * fmaf(gf, cp, gi * gg));
     tc = (1.f - ec) * rcp_ftz_(1.f + ec);
 }
 
@@ -154,9 +157,9 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, 512);
-    for (int i = tid; i < kGateCols; i += kFThreads) tail->bias[i] = p.bias[i];
+    for (int i = tid; i < kGateCols; i += kFThreads) tail->bias[i] = p.bias[i] * gate_scale(i);
     if (p.wih != nullptr)
-        for (int i = tid; i < p.c_in * kGateCols; i += kFThreads) tail->wih[i] = p.wih[i];
+        for (int i = tid; i < p.c_in * kGateCols; i += kFThreads) tail->wih[i] = p.wih[i] * gate_scale(i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -259,11 +262,17 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
         // end of a tile exposed the full DRAM latency at the top of the next one: ncu showed 21 % of the samples there)
         float cpv[16];
         float xs[kMaxC], xs_next[kMaxC];
+        // 32-bit element offsets (rows <= 2^25 is checked on the host): 64-bit address pairs cost registers, and the few
+        // that spilled were re-read from local memory in the tile loop at full L1-miss latency (ncu: 18 % of the samples)
+        const uint32_t row_in_tile = (uint32_t)(q * 32 + lane);
+        const uint32_t rows32 = (uint32_t)p.rows;
+        // tile-blocked (rows_pad x 64): element (tile, row, unit) at tile*8192 + (unit/8)*1024 + row*8 + unit%8
+        const uint32_t thr_c = row_in_tile * 8u + (uint32_t)part * 2048u;
         auto load_c4 = [&](int tile_n, int j) {
-            const int64_t rn = (int64_t)tile_n * kTileM + q * 32 + lane;
+            const uint32_t rn = (uint32_t)tile_n * kTileM + row_in_tile;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.c_prev != nullptr && tile_n < p.n_tiles && rn < p.rows)
-                v = *reinterpret_cast<const float4*>(p.c_prev + ws_off(rn, part * 16 + 4 * j));
+            if (p.c_prev != nullptr && tile_n < p.n_tiles && rn < rows32)
+                v = *reinterpret_cast<const float4*>(p.c_prev + ((uint32_t)tile_n * 8192u + thr_c + (uint32_t)(j >> 1) * 1024u + (uint32_t)(j & 1) * 4u));
             cpv[4 * j] = v.x; cpv[4 * j + 1] = v.y; cpv[4 * j + 2] = v.z; cpv[4 * j + 3] = v.w;
         };
         auto load_xs = [&](int tile_n, float (&dst)[kMaxC]) {
@@ -277,12 +286,13 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
 #pragma unroll
         for (int j = 0; j < 4; ++j) load_c4((int)blockIdx.x, j);
         if (l0) load_xs((int)blockIdx.x, xs);
-        for (int i = 0; i < my_tiles; ++i) {
-            const int tile = blockIdx.x + i * gridDim.x;
+        const int gstep = (int)gridDim.x;
+        int tile = (int)blockIdx.x;                // carried in a register: re-reading %ctaid every tile is a long-scoreboard stall
+        for (int i = 0; i < my_tiles; ++i, tile += gstep) {
             const int a = i & 1;
             const uint32_t aph = (uint32_t)(i >> 1) & 1;
-            const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
-            const bool valid = r < p.rows;
+            const uint32_t r = (uint32_t)tile * kTileM + row_in_tile;
+            const bool valid = r < rows32;
             if (p.nseg > 0) {
                 mbar_wait(&tail->tmem_full[a], aph, 3);
                 tc_fence_after();
@@ -304,11 +314,11 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int col = 4 * (unit0 + u);
-                    const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[col]);
-                    float pi = __uint_as_float(v[4 * u + 0]) + bv.x;
-                    float pf = __uint_as_float(v[4 * u + 1]) + bv.y;
-                    float pg = __uint_as_float(v[4 * u + 2]) + bv.z;
-                    float po = __uint_as_float(v[4 * u + 3]) + bv.w;
+                    const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[col]);      // pre-scaled (gate_scale)
+                    float pi = fmaf(__uint_as_float(v[4 * u + 0]), -1.4426950408889634f, bv.x);
+                    float pf = fmaf(__uint_as_float(v[4 * u + 1]), -1.4426950408889634f, bv.y);
+                    float pg = fmaf(__uint_as_float(v[4 * u + 2]), -2.8853900817779268f, bv.z);
+                    float po = fmaf(__uint_as_float(v[4 * u + 3]), -1.4426950408889634f, bv.w);
                     if (l0) {
 #pragma unroll
                         for (int c = 0; c < kMaxC; ++c)
@@ -328,12 +338,13 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                     hi[2 * pc + 1] = pack_bf16x2(hn[2], hn[3]);
                 }
                 if (valid) {
-                    *reinterpret_cast<float4*>(p.c_out + ws_off(r, unit0)) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    *reinterpret_cast<float4*>(p.c_out + ((uint32_t)tile * 8192u + thr_c + (uint32_t)(pc >> 1) * 1024u + (uint32_t)(pc & 1) * 4u)) =
+                        make_float4(cn[0], cn[1], cn[2], cn[3]);
                     if (p.h_f32 != nullptr)
-                        *reinterpret_cast<float4*>(p.h_f32 + r * kHid + unit0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                        *reinterpret_cast<float4*>(p.h_f32 + (r * (uint32_t)kHid + (uint32_t)unit0)) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                 }
-                load_c4(tile + (int)gridDim.x, pc);             // this piece's registers are free: next tile's values
-                if (l0 && pc == 0) load_xs(tile + (int)gridDim.x, xs_next);
+                load_c4(tile + gstep, pc);                      // this piece's registers are free: next tile's values
+                if (l0 && pc == 0) load_xs(tile + gstep, xs_next);
             }
             if (p.nseg > 0) {          // all TMEM reads of this accumulator are done (one mbarrier arrival per warp: 512
                 tc_fence_before();     // per-thread arrivals are 512 serialised shared-memory atomics per tile)
@@ -341,11 +352,11 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                 if (lane == 0) mbar_arrive(&tail->tmem_empty[a]);
             }
             if (valid) {
-                uint4* dh = reinterpret_cast<uint4*>(p.h_hi + r * kHid + part * 16);
+                uint4* dh = reinterpret_cast<uint4*>(p.h_hi + (r * (uint32_t)kHid + (uint32_t)part * 16u));
                 dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                 if (PLANES == 2) {
-                    uint4* dl = reinterpret_cast<uint4*>(p.h_lo + r * kHid + part * 16);
+                    uint4* dl = reinterpret_cast<uint4*>(p.h_lo + (r * (uint32_t)kHid + (uint32_t)part * 16u));
                     dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
@@ -409,7 +420,7 @@ __global__ void lstm16_pack_kernel(const float* __restrict__ w_ih, const float* 
 // read-modify-writes (no atomics; the slice layout is the accumulator's register layout); stmgcn_lstm16_wgrad_reduce sums
 // the slices once per layer and writes nn.LSTM-native gradients.
 constexpr int kBCompWarps = 16;
-constexpr int kBThreads = (kBCompWarps + 2) * 32;       // + MMA warp + producer warp
+constexpr int kBThreads = (kBCompWarps + 4) * 32;       // + three MMA-issuing warps + producer warp
 constexpr int kBWStages = 3;
 constexpr int kBWChunkTile = 64 * 128;                  // [64 gate cols][64 k] bf16 = 8 KB
 constexpr int kBWStageBytes = 4 * kBWChunkTile;         // (seg0 hi | seg0 lo | seg1 hi | seg1 lo) = 32 KB
@@ -418,7 +429,7 @@ constexpr int kBSgMax = 1024;
 struct B16Tail {
     float bias[kGateCols];
     float wih[kMaxC * kGateCols];
-    float s_db[kGateCols];
+    float s_db[kBCompWarps][kGateCols];        // per-compute-warp private bias-gradient partial sums (plain adds, no atomics)
     float s_ds[kBSgMax];
     uint64_t a_full, a_empty;
     uint64_t w_full[kBWStages], w_empty[kBWStages];
@@ -473,7 +484,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     const int warp = tid >> 5;
     const int lane = tid & 31;
     constexpr int kMmaWarp = kBCompWarps;
-    constexpr int kProdWarp = kBCompWarps + 1;
+    constexpr int kProdWarp = kBCompWarps + 3;
     constexpr int kCompThreads = kBCompWarps * 32;
     constexpr uint32_t kWgCol = 0, kDgCol = 256, kRcCol = 384;     // TMEM columns: weight grad | data grad | recompute x2
 
@@ -489,19 +500,17 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             mbar_init(&tail->r_empty[b], kBCompWarps);         // one arrival per compute warp
         }
         mbar_init(&tail->d_full, kBCompWarps);
-        mbar_init(&tail->d_empty, 1);
+        mbar_init(&tail->d_empty, 2);                          // weight-gradient warp + data-gradient warp
         mbar_init(&tail->g_full, 1);
         mbar_init(&tail->g_empty, kBCompWarps);
         mbar_init(&tail->done, 1);
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, 512);
-    for (int i = tid; i < kGateCols; i += kBThreads) {
-        tail->bias[i] = p.bias[i];
-        tail->s_db[i] = 0.f;
-    }
+    for (int i = tid; i < kGateCols; i += kBThreads) tail->bias[i] = p.bias[i] * gate_scale(i);
+    for (int i = tid; i < kBCompWarps * kGateCols; i += kBThreads) (&tail->s_db[0][0])[i] = 0.f;
     if (L0) {
-        for (int i = tid; i < p.c_in * kGateCols; i += kBThreads) tail->wih[i] = p.wih[i];
+        for (int i = tid; i < p.c_in * kGateCols; i += kBThreads) tail->wih[i] = p.wih[i] * gate_scale(i);
         for (int i = tid; i < kBSgMax; i += kBThreads) tail->s_ds[i] = 0.f;
     }
     tc_fence_before();
@@ -562,12 +571,16 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             }
         }
         TC_PROF_FLUSH(5, lane == 0)
-    } else if (warp == kMmaWarp) {
-        // ===================== MMA issuer =====================
+    } else if (warp >= kMmaWarp && warp < kProdWarp) {
+        // ===================== three MMA issuers: recompute (R) | weight gradient (W) | data gradient (D) =====================
+        // A tile needs ~240 tcgen05.mma instructions; issued by ONE thread they cost ~90 cycles apiece (ptxas moves every
+        // descriptor from vector to uniform registers around each UTCHMMA: measured 66 % of that warp's lifetime, 21 k cycles
+        // per tile against 9.2 k cycles of tensor-pipe work).  The three GEMMs write disjoint TMEM accumulators, so each gets
+        // its own issuing warp; tcgen05.commit tracks the issuing thread's MMAs, so every hand-off barrier is committed by
+        // the warp whose MMAs it guards (the dA buffer is released by W and D together: count 2).
+        // Everything that does not change is hoisted into 64-bit descriptor constants; a k-step is one add on the
+        // descriptor's address field (encoded address = bytes >> 4; all operands live below 256 KB: no carry).
         TC_PROF_DECL
-        // One thread issues ~240 MMAs per tile: everything that does not change is hoisted into 64-bit descriptor
-        // constants, and a k-step is a single add on the descriptor's address field (the encoded address is bytes >> 4;
-        // all operands live below 256 KB, so the 14-bit field cannot carry).
         constexpr uint32_t idesc_rc = idesc_bf16(kTileM, 64);              // recompute: A K-major, B K-major, N = 64
         constexpr uint32_t idesc_wg = idesc_bf16(kTileM, 64, 1, 1);        // weight gradient: both MN-major, M = kd (128), N = 64
         const uint32_t idesc_dg = idesc_bf16(kTileM, 64 * (p.nseg > 0 ? p.nseg : 1), 0, 1);   // data gradient: B MN-major, N = 64 * nseg
@@ -575,110 +588,121 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         constexpr uint64_t kStepK = 2;                                     // K-major: 16 bf16 = 32 bytes
         constexpr uint64_t kStepMN = 2048 >> 4;                            // MN-major: 16 rows of 128 bytes
         constexpr uint64_t kTileEnc = kATileBytes >> 4, kChunkEnc = kBWChunkTile >> 4, kStageEnc = kBWStageBytes >> 4;
-        const uint64_t rc_a = desc16_k(a_u);                               // + (s*2 + plane) * kTileEnc
-        const uint64_t rc_b = desc16_k(w_u);                               // + stage * kStageEnc + (s*2 + plane) * kChunkEnc
-        const uint64_t wg_a = desc16_mn(a_u + wg_a0 * kATileBytes, wg_lbo);   // hi planes; lo: + kTileEnc
-        const uint64_t wg_b = desc16_mn(da_u, kATileBytes);                // dA hi; lo: + kTileEnc
-        const uint64_t dg_a = desc16_k(da_u);                              // dA hi; lo: + kTileEnc
-        const uint64_t dg_b = desc16_mn(w_u, 2 * kBWChunkTile);            // + stage * kStageEnc (+ kChunkEnc for the lo plane)
-        const uint32_t t_rc = tmem_base + kRcCol, t_wg = tmem_base + kWgCol, t_dg = tmem_base + kDgCol;
         const int nseg = p.nseg;
-        uint32_t wc_r = 0;          // weight-chunk counter of the recompute front
-        uint32_t rc = 0;            // recompute-buffer counter
-        auto issue_R = [&]() {
-            const int stg = wc_r % kBWStages;
-            const uint32_t ph = (wc_r / kBWStages) & 1;
-            const int b = rc & 1;
-            const uint32_t bph = (rc >> 1) & 1;
-            mbar_wait_p(&tail->w_full[stg], ph, 0);
-            mbar_wait_p(&tail->r_empty[b], bph ^ 1, 2);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t d = t_rc + (uint32_t)b * 64;
-                const uint64_t bs = rc_b + (uint64_t)stg * kStageEnc;
+        const int role = warp - kMmaWarp;                                  // 0: R, 1: W, 2: D
+        if (role == 0) {
+            // ---- R: G_c[128 x 64] = [h_below | h_prev] . Wp[:, chunk c]  into one of two TMEM buffers ----
+            const uint64_t rc_a = desc16_k(a_u);                           // + (s*2 + plane) * kTileEnc
+            const uint64_t rc_b = desc16_k(w_u);                           // + stage * kStageEnc + (s*2 + plane) * kChunkEnc
+            const uint32_t t_rc = tmem_base + kRcCol;
+            uint32_t wc = 0;
+            if (nseg > 0) {
+                for (int i = 0; i < my_tiles; ++i) {
+                    mbar_wait_p(&tail->a_full, (uint32_t)i & 1, 3);
+                    for (int c = 0; c < 4; ++c, ++wc) {
+                        const int stg = wc % kBWStages;
+                        const uint32_t ph = (wc / kBWStages) & 1;
+                        const int b = wc & 1;
+                        const uint32_t bph = (wc >> 1) & 1;
+                        mbar_wait_p(&tail->w_full[stg], ph, 0);
+                        mbar_wait_p(&tail->r_empty[b], bph ^ 1, 2);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t d = t_rc + (uint32_t)b * 64;
+                            const uint64_t bs = rc_b + (uint64_t)stg * kStageEnc;
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    if (s < nseg) {
-                        const uint64_t a_hi = rc_a + (uint64_t)(s * 2) * kTileEnc, a_lo = a_hi + kTileEnc;
-                        const uint64_t b_hi = bs + (uint64_t)(s * 2) * kChunkEnc, b_lo = b_hi + kChunkEnc;
+                            for (int s = 0; s < 2; ++s) {
+                                if (s < nseg) {
+                                    const uint64_t a_hi = rc_a + (uint64_t)(s * 2) * kTileEnc, a_lo = a_hi + kTileEnc;
+                                    const uint64_t b_hi = bs + (uint64_t)(s * 2) * kChunkEnc, b_lo = b_hi + kChunkEnc;
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            mma_bf16(d, a_hi + kk * kStepK, b_hi + kk * kStepK, idesc_rc, (s > 0 || kk > 0) ? 1u : 0u);
-                        if (PLANES == 2) {
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        mma_bf16(d, a_hi + kk * kStepK, b_hi + kk * kStepK, idesc_rc, (s > 0 || kk > 0) ? 1u : 0u);
+                                    if (PLANES == 2) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) mma_bf16(d, a_lo + kk * kStepK, b_hi + kk * kStepK, idesc_rc, 1u);
+                                        for (int kk = 0; kk < 4; ++kk) mma_bf16(d, a_lo + kk * kStepK, b_hi + kk * kStepK, idesc_rc, 1u);
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) mma_bf16(d, a_hi + kk * kStepK, b_lo + kk * kStepK, idesc_rc, 1u);
+                                        for (int kk = 0; kk < 4; ++kk) mma_bf16(d, a_hi + kk * kStepK, b_lo + kk * kStepK, idesc_rc, 1u);
+                                    }
+                                }
+                            }
+                            mma_commit(&tail->r_full[b]);
                         }
+                        __syncwarp();
                     }
                 }
-                mma_commit(&tail->r_full[b]);
             }
-            __syncwarp();
-            ++wc_r;
-            ++rc;
-        };
-        uint32_t wc_d = 0;          // weight-chunk counter of the data-gradient front
-        uint32_t dcount = 0;        // dA chunks consumed
-        for (int i = 0; i < my_tiles; ++i) {
-            if (nseg > 0) {
-                mbar_wait_p(&tail->a_full, (uint32_t)i & 1, 3);
-                tc_fence_after();
-                issue_R();
-                issue_R();
-            }
-            for (int c = 0; c < 4; ++c, ++dcount) {
-                mbar_wait_p(&tail->d_full, dcount & 1, 1);
-                if (c == 0 && nseg > 0 && i > 0) mbar_wait_p(&tail->g_empty, (uint32_t)(i - 1) & 1, 2);
-                tc_fence_after();
-                if (lane == 0) {
-                    // ---- weight gradient: dWp[:, chunk c] += A'^T . dA_c   (M = kd 128, N = 64, K = 128 rows) ----
-                    const uint32_t d_wg = t_wg + (uint32_t)c * 64;
-                    {
-                        const uint32_t acc0 = (i > 0) ? 1u : 0u;
-                        mma_bf16(d_wg, wg_a, wg_b, idesc_wg, acc0);
+            TC_PROF_FLUSH(4, lane == 0)
+        } else if (role == 1) {
+            // ---- W: dWp[:, chunk c] += A'^T . dA_c   (M = kd 128, N = 64, K = 128 rows); one accumulator for the launch ----
+            const uint64_t wg_a = desc16_mn(a_u + wg_a0 * kATileBytes, wg_lbo);   // hi planes; lo: + kTileEnc
+            const uint64_t wg_b = desc16_mn(da_u, kATileBytes);                    // dA hi; lo: + kTileEnc
+            const uint32_t t_wg = tmem_base + kWgCol;
+            uint32_t dcount = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                for (int c = 0; c < 4; ++c, ++dcount) {
+                    mbar_wait_p(&tail->d_full, dcount & 1, 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t d_wg = t_wg + (uint32_t)c * 64;
+                        mma_bf16(d_wg, wg_a, wg_b, idesc_wg, (i > 0) ? 1u : 0u);
 #pragma unroll
                         for (int ks = 1; ks < 8; ++ks) mma_bf16(d_wg, wg_a + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, 1u);
                         if (PLANES == 2) {
 #pragma unroll
                             for (int ks = 0; ks < 8; ++ks)
                                 mma_bf16(d_wg, wg_a + kTileEnc + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, 1u);
-#pragma unroll
-                            for (int ks = 0; ks < 8; ++ks)
-                                mma_bf16(d_wg, wg_a + ks * kStepMN, wg_b + kTileEnc + ks * kStepMN, idesc_wg, 1u);
                         }
+                        // dA always has its lo plane (it never leaves the SM, the extra pass is free on an idle tensor pipe):
+                        // in the single-plane (bf16 storage) mode only the STORED operands are rounded to bf16
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_bf16(d_wg, wg_a + ks * kStepMN, wg_b + kTileEnc + ks * kStepMN, idesc_wg, 1u);
+                        if (c == 3 && nseg > 0) mma_commit(&tail->a_empty);        // A planes may be refilled
+                        mma_commit(&tail->d_empty);
                     }
-                    if (c == 3 && nseg > 0) mma_commit(&tail->a_empty);            // A planes may be refilled
-                    // ---- data gradient: [dx_below | dh_prev] += dA_c . Wp[:, chunk c]^T   (N = 64 * nseg, K = 64) ----
-                    if (nseg > 0) {
-                        const int stg = wc_d % kBWStages;
-                        const uint64_t bs = dg_b + (uint64_t)stg * kStageEnc;
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            mma_bf16(t_dg, dg_a + kk * kStepK, bs + kk * kStepMN, idesc_dg, (c > 0 || kk > 0) ? 1u : 0u);
-                        if (PLANES == 2) {
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                mma_bf16(t_dg, dg_a + kTileEnc + kk * kStepK, bs + kk * kStepMN, idesc_dg, 1u);
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                mma_bf16(t_dg, dg_a + kk * kStepK, bs + kChunkEnc + kk * kStepMN, idesc_dg, 1u);
-                        }
-                        mma_commit(&tail->w_empty[stg]);
-                    }
-                    mma_commit(&tail->d_empty);
-                    if (c == 3 && nseg > 0) mma_commit(&tail->g_full);
-                }
-                __syncwarp();
-                if (nseg > 0) {
-                    ++wc_d;
-                    if (c + 2 < 4) issue_R();
+                    __syncwarp();
                 }
             }
+            if (lane == 0) mma_commit(&tail->done);
+            __syncwarp();
+            TC_PROF_FLUSH(6, lane == 0)
+        } else {
+            // ---- D: [dx_below | dh_prev] += dA_c . Wp[:, chunk c]^T   (N = 64 * nseg, K = 64) ----
+            const uint64_t dg_a = desc16_k(da_u);                              // dA hi; lo: + kTileEnc
+            const uint64_t dg_b = desc16_mn(w_u, 2 * kBWChunkTile);            // + stage * kStageEnc (+ kChunkEnc: lo plane)
+            const uint32_t t_dg = tmem_base + kDgCol;
+            uint32_t dcount = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                for (int c = 0; c < 4; ++c, ++dcount) {
+                    mbar_wait_p(&tail->d_full, dcount & 1, 1);
+                    if (c == 0 && nseg > 0 && i > 0) mbar_wait_p(&tail->g_empty, (uint32_t)(i - 1) & 1, 2);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        if (nseg > 0) {
+                            const int stg = dcount % kBWStages;
+                            const uint64_t bs = dg_b + (uint64_t)stg * kStageEnc;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                mma_bf16(t_dg, dg_a + kk * kStepK, bs + kk * kStepMN, idesc_dg, (c > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)                       // dA lo plane: always (see the W warp)
+                                mma_bf16(t_dg, dg_a + kTileEnc + kk * kStepK, bs + kk * kStepMN, idesc_dg, 1u);
+                            if (PLANES == 2) {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    mma_bf16(t_dg, dg_a + kk * kStepK, bs + kChunkEnc + kk * kStepMN, idesc_dg, 1u);
+                            }
+                            mma_commit(&tail->w_empty[stg]);
+                        }
+                        mma_commit(&tail->d_empty);
+                        if (c == 3 && nseg > 0) mma_commit(&tail->g_full);
+                    }
+                    __syncwarp();
+                }
+            }
+            TC_PROF_FLUSH(7, lane == 0)
         }
-        if (lane == 0) mma_commit(&tail->done);
-        __syncwarp();
-        TC_PROF_FLUSH(4, lane == 0)
     } else {
         // ===================== compute warps =====================
         TC_PROF_DECL
@@ -691,13 +715,15 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         // raw inputs of one chunk: c_prev, dh_in, dh_rec, dc of this thread's 4 units
         struct Raw { float4 cp, dhi, dhr, dcv; };
         // tile-blocked workspaces: element (tile, row, unit) at tile*8192 + (unit/8)*1024 + row*8 + unit%8
-        const int64_t thr_off = (int64_t)(q * 32 + lane) * 8 + (part >> 1) * 1024 + (part & 1) * 4;
+        const uint32_t row_in_tile = (uint32_t)(q * 32 + lane);
+        const uint32_t rows32 = (uint32_t)p.rows;       // (rows <= 2^25 is checked on the host: 32-bit element offsets)
+        const uint32_t thr_off = row_in_tile * 8u + (uint32_t)(part >> 1) * 1024u + (uint32_t)(part & 1) * 4u;
         auto load_raw = [&](int tile, int c, Raw& rw) {
-            const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
+            const uint32_t r = (uint32_t)tile * kTileM + row_in_tile;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             rw.cp = rw.dhi = rw.dhr = rw.dcv = z;
-            if (tile < p.n_tiles && r < p.rows) {
-                const int64_t o = (int64_t)tile * (kTileM * kHid) + c * 2048 + thr_off;
+            if (tile < p.n_tiles && r < rows32) {
+                const uint32_t o = (uint32_t)tile * 8192u + (uint32_t)c * 2048u + thr_off;
                 if (p.c_prev) rw.cp = *reinterpret_cast<const float4*>(p.c_prev + o);
                 if (p.dh_in) rw.dhi = *reinterpret_cast<const float4*>(p.dh_in + o);
                 if (!p.first) {
@@ -706,9 +732,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 }
             }
         };
-        auto drain = [&](int i_prev) {          // [dx_below | dh_prev] of tile i_prev: TMEM -> tile-blocked workspaces
-            const int tile = blockIdx.x + i_prev * gridDim.x;
-            const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
+        auto drain = [&](int i_prev, int tile_prev) {   // [dx_below | dh_prev] of tile i_prev: TMEM -> tile-blocked workspaces
+            const uint32_t r = (uint32_t)tile_prev * kTileM + row_in_tile;
             mbar_wait(&tail->g_full, (uint32_t)i_prev & 1, 2);
             tc_fence_after();
             const int ncols = 64 * p.nseg;
@@ -721,10 +746,12 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 const bool is_dx = !L0 && col < 64;
                 float* base = is_dx ? p.dx_out : p.dh_rec;
                 const int unit0 = col & 63;
-                if (r < p.rows && base != nullptr && (is_dx || p.store_dh)) {
+                if (r < rows32 && base != nullptr && (is_dx || p.store_dh)) {
+                    const uint32_t o = (uint32_t)tile_prev * 8192u + row_in_tile * 8u + (uint32_t)(unit0 >> 3) * 1024u;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<uint4*>(base + ws_off(r, unit0 + 4 * j)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j)          // units unit0 + 4j: (j >> 1) 8-unit groups on, half (j & 1)
+                        *reinterpret_cast<uint4*>(base + (o + (uint32_t)(j >> 1) * 1024u + (uint32_t)(j & 1) * 4u)) =
+                            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
             }
             tc_fence_before();
@@ -732,22 +759,24 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             if (lane == 0) mbar_arrive(&tail->g_empty);
         };
         Raw cur, nxt;
-        load_raw((int)blockIdx.x, 0, nxt);
-        for (int i = 0; i < my_tiles; ++i) {
-            const int tile = blockIdx.x + i * gridDim.x;
-            const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
-            const bool valid = r < p.rows;
+        const int gstep = (int)gridDim.x;
+        int tile = (int)blockIdx.x;
+        load_raw(tile, 0, nxt);
+        float* my_db = tail->s_db[warp];           // this warp's private bias-gradient accumulators (no atomics)
+        for (int i = 0; i < my_tiles; ++i, tile += gstep) {
+            const uint32_t r = (uint32_t)tile * kTileM + row_in_tile;
+            const bool valid = r < rows32;
             if (L0) {
                 float sv = 0.f;
-                if (valid) sv = p.sg[(r % p.b_inner) * p.t_len + p.t];
+                if (valid) sv = p.sg[((int64_t)r % p.b_inner) * p.t_len + p.t];
 #pragma unroll
                 for (int c = 0; c < kMaxC; ++c) {
-                    xraw[c] = (valid && c < p.c_in) ? p.xo[(r * p.t_len + p.t) * p.c_in + c] : 0.f;
+                    xraw[c] = (valid && c < p.c_in) ? p.xo[((int64_t)r * p.t_len + p.t) * p.c_in + c] : 0.f;
                     xs[c] = xraw[c] * sv;
                     dxs[c] = 0.f;
                 }
             }
-            if (i > 0 && p.nseg > 0) drain(i - 1);
+            if (i > 0 && p.nseg > 0) drain(i - 1, tile - gstep);
             if (have_aux && part == 0) {
                 // auxiliary weight-gradient operand: tile 2 (hi) / tile 3 (lo), row = this thread's row, columns 0..C-1 = x*s
                 if (i > 0 && p.nseg > 0) mbar_wait(&tail->a_empty, (uint32_t)(i - 1) & 1, 3);
@@ -763,7 +792,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             for (int c = 0; c < 4; ++c, ++dcount) {
                 cur = nxt;
                 if (c < 3) load_raw(tile, c + 1, nxt);
-                else load_raw(tile + (int)gridDim.x, 0, nxt);
+                else load_raw(tile + gstep, 0, nxt);
                 uint32_t v[16];
                 if (p.nseg > 0) {
                     const int b = rcount & 1;
@@ -788,11 +817,11 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int col = 4 * (unit0 + u);
-                    const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[col]);
-                    float pi = __uint_as_float(v[4 * u + 0]) + bv.x;
-                    float pf = __uint_as_float(v[4 * u + 1]) + bv.y;
-                    float pg = __uint_as_float(v[4 * u + 2]) + bv.z;
-                    float po = __uint_as_float(v[4 * u + 3]) + bv.w;
+                    const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[col]);      // pre-scaled (gate_scale)
+                    float pi = fmaf(__uint_as_float(v[4 * u + 0]), -1.4426950408889634f, bv.x);
+                    float pf = fmaf(__uint_as_float(v[4 * u + 1]), -1.4426950408889634f, bv.y);
+                    float pg = fmaf(__uint_as_float(v[4 * u + 2]), -2.8853900817779268f, bv.z);
+                    float po = fmaf(__uint_as_float(v[4 * u + 3]), -1.4426950408889634f, bv.w);
                     if (L0) {
 #pragma unroll
                         for (int cc = 0; cc < kMaxC; ++cc)
@@ -804,8 +833,9 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     }
                     float gi, gf, gg, go, tc_;
                     lstm_cell_gates8(pi, pf, pg, po, cp[u], gi, gf, gg, go, tc_);
-                    const float dh = valid ? (dhr[u] + dhi[u]) : 0.f;
-                    const float dcv = valid ? fmaf(dh * go, 1.f - tc_ * tc_, dci[u]) : 0.f;
+                    // rows past the end: load_raw returned zeros for dh_rec / dh_in / dc, so dh = dcv = 0 and dA = 0 without selects
+                    const float dh = dhr[u] + dhi[u];
+                    const float dcv = fmaf(dh * go, 1.f - tc_ * tc_, dci[u]);
                     da[4 * u + 0] = dcv * gg * gi * (1.f - gi);
                     da[4 * u + 1] = dcv * cp[u] * gf * (1.f - gf);
                     da[4 * u + 2] = dcv * gi * (1.f - gg * gg);
@@ -815,18 +845,17 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
 #pragma unroll
                         for (int cc = 0; cc < kMaxC; ++cc)
                             if (cc < p.c_in) {
+                                // W_ih is stored pre-scaled: undo -log2(e) (and the g gate's extra factor 2)
                                 const float4 wv = *reinterpret_cast<const float4*>(&tail->wih[cc * kGateCols + col]);
-                                dxs[cc] += da[4 * u] * wv.x + da[4 * u + 1] * wv.y + da[4 * u + 2] * wv.z + da[4 * u + 3] * wv.w;
+                                dxs[cc] = fmaf(da[4 * u] * wv.x + da[4 * u + 1] * wv.y + 0.5f * (da[4 * u + 2] * wv.z) + da[4 * u + 3] * wv.w,
+                                               -0.6931471805599453f, dxs[cc]);
                             }
                     }
                 }
                 // dA chunk -> bf16 planes, 128-byte-swizzled tile: row = this thread's row, columns 16*part .. +15
                 uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (PLANES == 2) split_bf16x2(da[2 * j], da[2 * j + 1], hi[j], lo[j]);
-                    else hi[j] = pack_bf16x2(da[2 * j], da[2 * j + 1]);
-                }
+                for (int j = 0; j < 8; ++j) split_bf16x2(da[2 * j], da[2 * j + 1], hi[j], lo[j]);
                 if (dcount > 0) mbar_wait(&tail->d_empty, (dcount - 1) & 1, 0);     // W_{c-1}, D_{c-1} have read the dA tile
                 {
                     const uint32_t row = (uint32_t)(q * 32 + lane);
@@ -834,16 +863,14 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     const uint32_t o1 = row * 128u + ((((uint32_t)(2 * part + 1)) ^ (row & 7u)) << 4);
                     *reinterpret_cast<uint4*>(da_sm + o0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4*>(da_sm + o1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    if (PLANES == 2) {
-                        *reinterpret_cast<uint4*>(da_sm + kATileBytes + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                        *reinterpret_cast<uint4*>(da_sm + kATileBytes + o1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-                    }
+                    *reinterpret_cast<uint4*>(da_sm + kATileBytes + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(da_sm + kATileBytes + o1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tail->d_full);
                 if (valid)
-                    *reinterpret_cast<float4*>(p.dc + (int64_t)tile * (kTileM * kHid) + c * 2048 + thr_off) =
+                    *reinterpret_cast<float4*>(p.dc + ((uint32_t)tile * 8192u + (uint32_t)c * 2048u + thr_off)) =
                         make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
                 // bias gradient: column sums over the warp's 32 rows by a halving butterfly (16 shuffles), then one
                 // shared-memory atomic per column from the even lanes
@@ -874,9 +901,9 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                         s1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
                     }
                     s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-                    if ((lane & 1) == 0) {
+                    if ((lane & 1) == 0) {         // (shared-memory float atomics compile to CAS spin loops: private rows instead)
                         const int j = (u16 ? 8 : 0) + (u8 ? 4 : 0) + (u4 ? 2 : 0) + (u2 ? 1 : 0);
-                        atomicAdd(&tail->s_db[4 * unit0 + j], s1);
+                        my_db[4 * unit0 + j] += s1;
                     }
                 }
             }
@@ -885,12 +912,12 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 float contrib = 0.f;
 #pragma unroll
                 for (int cc = 0; cc < kMaxC; ++cc) contrib += dxs[cc] * xraw[cc];
-                const int64_t b = r % p.b_inner;
+                const int64_t b = (int64_t)r % p.b_inner;
                 if (p.b_inner <= kBSgMax) atomicAdd(&tail->s_ds[b], contrib);
                 else atomicAdd(&p.d_s[b * p.t_len + p.t], contrib);
             }
         }
-        if (my_tiles > 0 && p.nseg > 0) drain(my_tiles - 1);
+        if (my_tiles > 0 && p.nseg > 0) drain(my_tiles - 1, tile - gstep);
         TC_PROF_FLUSH(3, tid == 0)
         // ---- weight-gradient accumulator -> this CTA's scratch slice (register layout: [part][piece][vec][row m][4]) ----
         if (my_tiles > 0) {
@@ -926,7 +953,12 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
-    for (int i = tid; i < kGateCols; i += kBThreads) atomicAdd(&p.dbp[i], tail->s_db[i]);
+    for (int i = tid; i < kGateCols; i += kBThreads) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBCompWarps; ++w) v += tail->s_db[w][i];
+        atomicAdd(&p.dbp[i], v);
+    }
     if (L0 && p.b_inner <= kBSgMax)
         for (int i = tid; i < (int)p.b_inner; i += kBThreads) atomicAdd(&p.d_s[(int64_t)i * p.t_len + p.t], tail->s_ds[i]);
 }
@@ -1032,7 +1064,7 @@ extern "C" int32_t stmgcn_lstm16_step_fwd(int32_t t, int32_t t_len, int32_t n_la
     STMGCN_REQUIRE(planes == 1 || planes == 2, STMGCN_ERR_ARG, "lstm16_step_fwd: planes=%d", planes);
     STMGCN_REQUIRE(t >= 0 && t < t_len && n_layers >= 1 && n_layers <= 8 && rows > 0 && c_in >= 1 && c_in <= kMaxC && b_inner > 0,
                    STMGCN_ERR_SHAPE, "lstm16_step_fwd: t=%d T=%d L=%d rows=%lld C=%d", t, t_len, n_layers, (long long)rows, c_in);
-    STMGCN_REQUIRE(rows <= 0x7fffff00LL, STMGCN_ERR_SHAPE, "lstm16_step_fwd: rows=%lld too large", (long long)rows);
+    STMGCN_REQUIRE(rows <= (1LL << 25), STMGCN_ERR_SHAPE, "lstm16_step_fwd: rows=%lld too large (32-bit element offsets)", (long long)rows);
     STMGCN_REQUIRE((h0p == nullptr) == (c0 == nullptr), STMGCN_ERR_ARG, "lstm16_step_fwd: h0p and c0 go together");
     cudaStream_t st = (cudaStream_t)stream;
     const int n_tiles = (int)ceil_div(rows, kTileM);
@@ -1114,7 +1146,7 @@ extern "C" int32_t stmgcn_lstm16_step_bwd(int32_t t, int32_t t_len, int32_t n_la
     STMGCN_REQUIRE(planes == 1 || planes == 2, STMGCN_ERR_ARG, "lstm16_step_bwd: planes=%d", planes);
     STMGCN_REQUIRE(t >= 0 && t < t_len && n_layers >= 1 && n_layers <= 8 && rows > 0 && c_in >= 1 && c_in <= kMaxC && b_inner > 0,
                    STMGCN_ERR_SHAPE, "lstm16_step_bwd: t=%d T=%d L=%d rows=%lld C=%d", t, t_len, n_layers, (long long)rows, c_in);
-    STMGCN_REQUIRE(rows <= 0x7fffff00LL, STMGCN_ERR_SHAPE, "lstm16_step_bwd: rows=%lld too large", (long long)rows);
+    STMGCN_REQUIRE(rows <= (1LL << 25), STMGCN_ERR_SHAPE, "lstm16_step_bwd: rows=%lld too large (32-bit element offsets)", (long long)rows);
     STMGCN_REQUIRE((h0p == nullptr) == (c0 == nullptr), STMGCN_ERR_ARG, "lstm16_step_bwd: h0p and c0 go together");
     cudaStream_t st = (cudaStream_t)stream;
     const int n_tiles = (int)ceil_div(rows, kTileM);

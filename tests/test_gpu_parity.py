@@ -334,3 +334,41 @@ def test_projection_tensor_core_path_matches_exact_fp32_path(ks):
         ops.set_lstm_path(old)
     for name, a, c in zip(("out", "dx", "dW", "db"), res["tc"], res["fma"]):
         assert_close(a.cpu().numpy(), c.cpu().numpy(), f"proj tc vs fma {name}", 2e-5)
+
+
+def test_bf16_arithmetic_mode_within_the_reference_bf16_tolerance():
+    """STMGCN_LSTM_PLANES=1 / ops.set_lstm_planes(1): hidden states are stored as ONE bf16 plane and the shared LSTM's
+    tensor-core products with them run single-pass (fp32 cell state, accumulation and on-chip dA) -- the arithmetic of the
+    bf16-quoted BASELINE configs.  The 1e-4 bar is an fp32 statement; SURVEY.md section 8(d) measured the reference's OWN
+    bf16 execution at 1.9-2.2e-2 from its fp32 output, which is the tolerance here.
+    Forward: against the reference's golden output (ReLU model).  Gradients: on the same model WITHOUT the GCN activation --
+    with ReLU, bf16-level noise in h flips ~1e-3 of the masks of a 37 k-element GCN output and moves the gradients of a
+    6-window batch by ~10 % (measured), which says nothing about the kernels; the smooth model isolates the arithmetic."""
+    from stmgcn_b200 import ops
+    meta, params, grads, supports, _, blob = load_golden("cfg3_small_ref")
+    x = torch.from_numpy(blob["x"]).to(DEV)
+    y = torch.from_numpy(blob["y"]).to(DEV)
+    sups = [s.to(DEV) for s in supports]
+    old = ops.lstm_planes()
+    try:
+        ops.set_lstm_planes(1)
+        model = build_model(meta, DEV)
+        model.load_state_dict(params)
+        with torch.no_grad():
+            out = model(obs_seq=x, sta_adj_list=sups)
+        smooth = build_model(meta, DEV, relu=False)
+        smooth.load_state_dict(params)
+        out_s = smooth(obs_seq=x, sta_adj_list=sups)
+        nn.MSELoss(reduction="mean")(out_s, y).backward()
+    finally:
+        ops.set_lstm_planes(old)
+    e_out = assert_close(out.cpu().numpy(), blob["out"], "bf16 mode forward (ReLU model, reference golden)", 2e-2)
+    orc = O.SparseOracle({k_: v.numpy() for k_, v in params.items()},
+                         [O.laplacian_csr_from_supports(s) for s in supports], meta["k"] + 1, relu=False, dtype=np.float64)
+    o_ref, _, g_ref = orc.loss_and_grads(blob["x"], blob["y"])
+    e_out_s = assert_close(out_s.detach().cpu().numpy(), o_ref, "bf16 mode forward (smooth model)", 2e-2)
+    errs = {key: assert_close(p.grad.cpu().numpy(), g_ref[key], f"bf16 mode grad {key}", 2e-2)
+            for key, p in smooth.named_parameters()}
+    print(f"bf16 arithmetic mode: forward error {e_out:.2e} (ReLU) / {e_out_s:.2e} (smooth); worst gradient error "
+          f"{max(errs.values()):.2e} ({max(errs, key=errs.get)}); tolerance 2e-2")
+    assert e_out > 1e-6, "the bf16 mode produced fp32-grade results: the single-pass path did not run"

@@ -18,7 +18,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "st-mgcn_b200"))
 from stmgcn_b200 import _lib, ops  # noqa: E402
 
-ROLES = {0: "fwd producer", 1: "fwd mma", 2: "fwd epilogue", 3: "bwd compute", 4: "bwd mma", 5: "bwd producer"}
+ROLES = {0: "fwd producer", 1: "fwd mma", 2: "fwd epilogue", 3: "bwd compute", 4: "bwd mma R", 6: "bwd mma W", 7: "bwd mma D", 5: "bwd producer"}
 
 
 def read(reset=True):
