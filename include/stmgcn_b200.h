@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define STMGCN_ABI_VERSION 1
+#define STMGCN_ABI_VERSION 2
 
 /* error codes < 0 */
 #define STMGCN_ERR_ARG      (-1)   /* null pointer / bad enum */
@@ -89,7 +89,7 @@ int32_t stmgcn_obs_to_node_major(const float* obs, float* xo, float* xt, int64_t
 int32_t stmgcn_proj_fwd(const float* s, int64_t stride_k, int32_t ks, int64_t rows, int32_t p,
                         const float* w, const float* bias, int32_t q, int32_t act, float* out,
                         float* pool, int64_t b_inner, const float* wimg, void* stream);
-/* Tensor-core operand images of W (ks*64, 64) for p = q = 64, ks <= 8 (3xTF32, see stmgcn_lstm_pack_tc):
+/* Tensor-core operand images of W (ks*64, 64) for p = q = 64, ks <= 8 (3xTF32: every fp32 operand split into tf32 hi + lo, three tcgen05 passes):
  * img_fwd: ks*64*64*2 floats; img_bwd (may be NULL): one 2*2*256*32-float image per group of 4 supports (two images
  * when ks > 4), ZERO-FILLED by the caller (rows beyond ks*64 stay zero).  Passing wimg / wimg_t != NULL to stmgcn_proj_fwd / _bwd selects the tcgen05 kernels when
  * p = q = 64 (and, for the backward, a full d_out and u are given); otherwise the exact-FFMA kernels run. */
@@ -113,61 +113,40 @@ int32_t stmgcn_gate_fwd(const float* pool, int64_t b, int32_t t, int64_t n_regio
 int32_t stmgcn_gate_bwd(const float* d_s, const float* z, const float* a1, const float* s, int64_t b,
                         int32_t t, const float* fcw, float* d_fcw, float* d_fcb, float* d_z, void* stream);
 
-/* ---- K3b: shared-weight LSTM, one call per timestep (STMGCN.py:44, :47-50; nn.LSTM semantics) -------
- * Weights are passed packed (the host packs once per step, see ops.py), H = hid, columns gate-interleaved
+/* ---- K3b (exact fp32, any H <= 128): shared-weight LSTM, one call per timestep (STMGCN.py:44, :47-50) ------------
+ * The CUDA-core path for every shape the tensor-core kernels below do not cover (H != 64 or C > 4), and the on-device
+ * reference the parity tests compare them with.  Weights are passed packed, H = hid, columns gate-interleaved
  * col = 4*unit + gate (gate order i,f,g,o):
  *   wx     : (C, 4H)      = W_ih_l0^T                      (layer-0 input weights)
  *   wp[l]  : (kd_l, 4H)   = W_hh_0^T (l = 0, kd_0 = H) or [W_ih_l^T ; W_hh_l^T] (l > 0, kd_l = 2H)
  *   bp[l]  : (4H)         = b_ih_l + b_hh_l
  *   wpt[l] : (4H, kd_l)   = wp[l]^T                        (backward data operand)
- * State / tape tensors, rows r = n*B + b:
+ * State / tape tensors, rows r = n*B + b, fp32 row-major:
  *   hs, cs: (L, T, R, H);  gates: (L, T, R, 4H) post-activation, gate-interleaved (NULL in inference);
- * xo: (R, T, C) node-major observations, s_gate: (B, T) context gate (the modulation xo * s is fused into
- * the layer-0 input read, STMGCN.py:44).  h0/c0: (L, R, H) or NULL (zeros, STMGCN.py:53-57).
- * wimg: optional per-layer tensor-core weight images (see stmgcn_lstm_pack_tc) or NULL.
- * blocked_cs != 0 (tensor-core kernels on every layer only): cs and c0 are tile-blocked like the backward
- * workspaces (see stmgcn_lstm_step_bwd), ceil(R/128)*128 rows per (layer, step) slice; hs stays row-major.
+ * xo: (R, T, C) node-major observations, s_gate: (B, T) context gate (the modulation xo * s is fused into the layer-0
+ * input read, STMGCN.py:44).  h0/c0: (L, R, H) or NULL (zeros, STMGCN.py:53-57).
  * Step t computes layers 0..L-1.  Limits: H % 4 == 0, H <= 128, C <= 4, L <= 8. */
 int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
                              const float* wx, const float* const* wp, const float* const* bp,
-                             const float* const* wimg, const float* h0, const float* c0, float* hs, float* cs,
-                             float* gates, int32_t blocked_cs, void* stream);
-/* Tensor-core operand images of one packed layer (H = 64 only): 32-wide k-blocks of [hi | lo] K-major
- * 128B-swizzled fp32 tiles holding the tf32 hi / lo split of the weights (3xTF32 scheme).
- *   img_fwd (kd_fwd*256*2 floats) from wp_fwd (kd_fwd, 4H): operand of gates = A . Wp (tiles [256][32]).
- *           Layers > 0: wp_fwd = wp[l], kd_fwd = 128.  Layer 0: the AUGMENTED operand (96, 4H) =
- *           [W_hh^T (64 rows) ; W_ih^T (C rows) ; b_ih + b_hh (1 row) ; zeros] -- the forward kernel feeds
- *           [h_prev | x*s | 1 | 0] so the input term and the bias come out of the MMA.
- *   img_bwd (kd_bwd*256*2 floats, may be NULL) from wp_bwd = wp[l] (kd_bwd = 64 or 128): operand of
- *           [dx | dh] = dA . Wp^T (tiles [kd][32]).
- * Passing wimg[l] / wimg_t[l] != NULL to stmgcn_lstm_step_fwd / _bwd selects the tcgen05 kernels for that layer;
- * NULL (or H != 64) runs the exact-FFMA kernels.  Both paths read and write the same tape. */
-int32_t stmgcn_lstm_pack_tc(const float* wp_fwd, int32_t kd_fwd, const float* wp_bwd, int32_t kd_bwd, int32_t hid,
-                            float* img_fwd, float* img_bwd, void* stream);
+                             const float* h0, const float* c0, float* hs, float* cs, float* gates, void* stream);
 /* BPTT step t (call t = T-1 .. 0).  d_top: (R, H) gradient of hs[L-1][T-1] (read at t = T-1 only).
  * Workspaces: dh_rec, dc: (L, R, H); dx_work: (R, H).  No initialisation is needed: the call with t = T-1 treats the
  * incoming dh_rec / dc as zero without reading them (h_n / c_n carry no gradient, STMGCN.py:113).
  * gates[l][t] is overwritten IN PLACE with the pre-activation gradients dA (stmgcn_lstm_wgrad reads them).
- * wimg_t: optional per-layer tensor-core images of Wp^T (stmgcn_lstm_pack_tc) or NULL.
- * blocked_ws != 0 (tensor-core kernels on every layer only): d_top, dh_rec, dc, dx_work AND cs / c0 are tile-blocked,
- * element (r, u) at (((r/128)*8 + u/8)*128 + r%128)*8 + u%8, with ceil(R/128)*128 rows per (layer) slice.
  * Accumulates (+=; caller zeroes): d_s (B,T) = sum_{n,c} dxmod * xo (gate adjoint, STMGCN.py:44),
  * dwx (C,4H), dbp[l] (4H). */
 int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
-                             const float* wx, const float* const* wpt, const float* const* wimg_t,
-                             const float* c0, const float* cs, float* gates, const float* d_top, float* dh_rec,
-                             float* dc, float* dx_work, float* d_s, float* dwx, float* const* dbp,
-                             int32_t blocked_ws, void* stream);
+                             const float* wx, const float* const* wpt, const float* c0, const float* cs,
+                             float* gates, const float* d_top, float* dh_rec, float* dc, float* dx_work,
+                             float* d_s, float* dwx, float* const* dbp, void* stream);
 /* weight gradients of one layer after all stmgcn_lstm_step_bwd calls:
- * dwp (kd_l, 4H) += [h_below_t | h_{t-1}]^T dA summed over all (t, r).  use_tc != 0 (and H = 64) runs the
- * tcgen05 3xTF32 kernel, otherwise the exact-FFMA reduction. */
+ * dwp (kd_l, 4H) += [h_below_t | h_{t-1}]^T dA summed over all (t, r). */
 int32_t stmgcn_lstm_wgrad(int32_t layer, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
-                          const float* h0, const float* hs, const float* gates_da, float* dwp,
-                          int32_t use_tc, void* stream);
+                          const float* h0, const float* hs, const float* gates_da, float* dwp, void* stream);
 
-/* ---- K3b, second generation (H = 64 only): bf16-plane tensor-core LSTM without a gate tape ---------------------
+/* ---- K3b on the tensor cores (H = 64, C <= 4): bf16-plane LSTM without a gate tape -----------------------------
  * Same arithmetic contract as stmgcn_lstm_step_fwd/_bwd/_wgrad (STMGCN.py:44, :47-50; nn.LSTM semantics, fp32 state and
  * accumulation), different tape:
  *   hp : (L, T, P, R, 64) bf16 -- every hidden state as P planes; P = 2: hi = bf16(h), lo = bf16(h - hi) (3-pass

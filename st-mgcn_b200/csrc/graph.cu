@@ -58,13 +58,6 @@ struct stmgcn_graph {
     int32_t* t_rowptr = nullptr;
     int32_t* t_colidx = nullptr;
     float* t_vals = nullptr;
-    // bank-aware sliced ELL (spmm.cu, strip kernel): [0] = A, [1] = A^T
-    bool has_ell[2] = {false, false};
-    int32_t n_slices = 0;
-    int32_t* ell_perm[2] = {nullptr, nullptr};      // (n_slices*32) row handled by (slice, lane); -1 = padding
-    int32_t* ell_off[2] = {nullptr, nullptr};       // (n_slices+1) entry offsets
-    uint2* ell_ent[2] = {nullptr, nullptr};         // entries {col, float bits}
-    int64_t ell_total[2] = {0, 0};
 };
 
 namespace {
@@ -179,148 +172,6 @@ int32_t build_transpose(stmgcn_graph* g, cudaStream_t st) {
 }
 
 
-// ---- bank-aware sliced ELL -------------------------------------------------------------------------------
-// Rows are sorted by length (descending) and cut into slices of 32 (one warp); slice s stores width_s slots x 32
-// lanes of {col, val}.  The strip kernel keeps an (N x 8 fp32) column strip of X in shared memory, row j at byte
-// 32*j; lane l reads the 16-byte half (l & 1) first.  Within one 8-lane LDS phase the 16-byte bank group of a lane
-// is (col mod 4)*2 + half, so a phase is conflict free iff its 4 even lanes (and its 4 odd lanes) gather columns
-// with 4 different residues mod 4.  The slot order of every row is therefore chosen per "quad" (the 4 same-parity
-// rows of a phase) by a greedy matching; padding slots (val = 0) take any free residue.
-__global__ void ell_rowlen_keys_kernel(int64_t n, const int32_t* __restrict__ rowptr, uint32_t* __restrict__ keys,
-                                       int32_t* __restrict__ ids) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    keys[i] = 0x7fffffffu - (uint32_t)(rowptr[i + 1] - rowptr[i]);     // ascending key = descending length
-    ids[i] = (int32_t)i;
-}
-
-__global__ void ell_widths_kernel(int64_t n, int32_t n_slices, const int32_t* __restrict__ rowptr,
-                                  const int32_t* __restrict__ perm_sorted, int32_t* __restrict__ perm_pad,
-                                  int32_t* __restrict__ widths32) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > n_slices) return;
-    if (s == n_slices) { widths32[s] = 0; return; }
-    const int r = perm_sorted[(int64_t)s * 32];                        // longest row of the slice comes first
-    widths32[s] = (rowptr[r + 1] - rowptr[r]) * 32;
-    for (int l = 0; l < 32; ++l) {
-        const int64_t idx = (int64_t)s * 32 + l;
-        perm_pad[idx] = idx < n ? perm_sorted[idx] : -1;
-    }
-}
-
-__global__ void ell_fill_kernel(int32_t n_slices, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                                const float* __restrict__ vals, const int32_t* __restrict__ perm_pad,
-                                const int32_t* __restrict__ off, uint2* __restrict__ ent) {
-    const int quad = blockIdx.x * blockDim.x + threadIdx.x;            // 8 quads per slice
-    if (quad >= n_slices * 8) return;
-    const int s = quad >> 3, g = (quad >> 1) & 3, par = quad & 1;
-    const int width = (off[s + 1] - off[s]) / 32;
-    int lane[4], beg[4], end[4], cur[4][4], cnt[4][4];
-    for (int j = 0; j < 4; ++j) {
-        lane[j] = 8 * g + par + 2 * j;
-        const int r = perm_pad[s * 32 + lane[j]];
-        beg[j] = r >= 0 ? rowptr[r] : 0;
-        end[j] = r >= 0 ? rowptr[r + 1] : 0;
-        for (int q = 0; q < 4; ++q) { cur[j][q] = beg[j]; cnt[j][q] = 0; }
-        for (int e = beg[j]; e < end[j]; ++e) cnt[j][colidx[e] & 3]++;
-        for (int q = 0; q < 4; ++q) {                                  // cursor q -> first entry with residue q
-            int e = beg[j];
-            while (e < end[j] && (colidx[e] & 3) != q) ++e;
-            cur[j][q] = e;
-        }
-    }
-    for (int k = 0; k < width; ++k) {
-        unsigned used = 0;                                             // residues taken in this slot
-        int order[4] = {0, 1, 2, 3};
-        int rem[4], key[4];
-        for (int j = 0; j < 4; ++j) {
-            rem[j] = cnt[j][0] + cnt[j][1] + cnt[j][2] + cnt[j][3];
-            key[j] = rem[j] == 0 ? 0x7fffffff : rem[j];                // rows with fewer choices first, finished rows last
-        }
-        for (int a = 0; a < 3; ++a)
-            for (int b2 = a + 1; b2 < 4; ++b2)
-                if (key[order[b2]] < key[order[a]]) { const int t = order[a]; order[a] = order[b2]; order[b2] = t; }
-        for (int a = 0; a < 4; ++a) {
-            const int j = order[a];
-            int pick = -1, best = 0;
-            for (int q = 0; q < 4; ++q)
-                if (!((used >> q) & 1) && cnt[j][q] > best) { best = cnt[j][q]; pick = q; }
-            uint2 e;
-            if (pick < 0 && rem[j] > 0) {                              // every free residue exhausted: accept a conflict
-                for (int q = 0; q < 4; ++q)
-                    if (cnt[j][q] > best) { best = cnt[j][q]; pick = q; }
-            }
-            if (pick >= 0) {
-                const int idx = cur[j][pick];
-                e.x = (uint32_t)colidx[idx];
-                e.y = __float_as_uint(vals[idx]);
-                int nx = idx + 1;
-                while (nx < end[j] && (colidx[nx] & 3) != pick) ++nx;
-                cur[j][pick] = nx;
-                cnt[j][pick]--;
-                used |= 1u << pick;
-            } else {                                                   // padding: zero weight, any free residue
-                int q = 0;
-                while (q < 3 && ((used >> q) & 1)) ++q;
-                e.x = (uint32_t)q;
-                e.y = 0u;
-                used |= 1u << q;
-            }
-            ent[(int64_t)off[s] + (int64_t)k * 32 + lane[j]] = e;
-        }
-    }
-}
-
-int32_t build_ell(stmgcn_graph* g, int orient, cudaStream_t st) {
-    const int64_t n = g->n;
-    const int32_t* rowptr = orient ? g->t_rowptr : g->rowptr;
-    const int32_t* colidx = orient ? g->t_colidx : g->colidx;
-    const float* vals = orient ? g->t_vals : g->vals;
-    if (n < 8 || getenv("STMGCN_SPMM_STRIP") == nullptr) return 0;     // only built for the opt-in strip kernel
-    const int32_t n_slices = (int32_t)ceil_div(n, 32);
-    g->n_slices = n_slices;
-    uint32_t *keys = nullptr, *keys_out = nullptr;
-    int32_t *ids = nullptr, *ids_out = nullptr, *widths = nullptr;
-    void* tmp = nullptr;
-    int32_t rc = 0;
-    do {
-        if ((rc = cudaMalloc(&keys, n * 4))) break;
-        if ((rc = cudaMalloc(&keys_out, n * 4))) break;
-        if ((rc = cudaMalloc(&ids, n * 4))) break;
-        if ((rc = cudaMalloc(&ids_out, n * 4))) break;
-        if ((rc = cudaMalloc(&widths, (n_slices + 1) * 4))) break;
-        if ((rc = cudaMalloc(&g->ell_perm[orient], (size_t)n_slices * 32 * 4))) break;
-        if ((rc = cudaMalloc(&g->ell_off[orient], (n_slices + 1) * 4))) break;
-        ell_rowlen_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, rowptr, keys, ids);
-        size_t bytes = 0;
-        if ((rc = cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys_out, ids, ids_out, (int)n, 0, 32, st))) break;
-        if ((rc = cudaMalloc(&tmp, bytes ? bytes : 16))) break;
-        if ((rc = cub::DeviceRadixSort::SortPairs(tmp, bytes, keys, keys_out, ids, ids_out, (int)n, 0, 32, st))) break;
-        ell_widths_kernel<<<(unsigned)ceil_div(n_slices + 1, 128), 128, 0, st>>>(n, n_slices, rowptr, ids_out,
-                                                                                 g->ell_perm[orient], widths);
-        if ((rc = exclusive_scan(widths, g->ell_off[orient], n_slices + 1, st))) break;
-        int32_t total = 0;
-        if ((rc = cudaMemcpyAsync(&total, g->ell_off[orient] + n_slices, 4, cudaMemcpyDeviceToHost, st))) break;
-        if ((rc = cudaStreamSynchronize(st))) break;
-        g->ell_total[orient] = total;
-        if ((rc = cudaMalloc(&g->ell_ent[orient], (size_t)(total ? total : 1) * sizeof(uint2)))) break;
-        ell_fill_kernel<<<(unsigned)ceil_div((int64_t)n_slices * 8, 64), 64, 0, st>>>(
-            n_slices, rowptr, colidx, vals, g->ell_perm[orient], g->ell_off[orient], g->ell_ent[orient]);
-        count_launch(12);
-        if ((rc = cudaStreamSynchronize(st))) break;
-        rc = check_launch("build_ell");
-    } while (0);
-    cudaFree(keys);
-    cudaFree(keys_out);
-    cudaFree(ids);
-    cudaFree(ids_out);
-    cudaFree(widths);
-    cudaFree(tmp);
-    if (rc > 0) return fail(rc, "ell build: %s", cudaGetErrorString((cudaError_t)rc));
-    if (rc == 0) g->has_ell[orient] = true;
-    return rc;
-}
-
 void free_graph(stmgcn_graph* g) {
     if (!g) return;
     cudaFree(g->rowptr);
@@ -329,11 +180,6 @@ void free_graph(stmgcn_graph* g) {
     cudaFree(g->t_rowptr);
     cudaFree(g->t_colidx);
     cudaFree(g->t_vals);
-    for (int o = 0; o < 2; ++o) {
-        cudaFree(g->ell_perm[o]);
-        cudaFree(g->ell_off[o]);
-        cudaFree(g->ell_ent[o]);
-    }
     delete g;
 }
 
@@ -374,8 +220,6 @@ int32_t stmgcn_graph_from_dense(stmgcn_graph_t** out, const float* dense, int64_
         count_launch();
         if ((rc = check_launch("graph_from_dense"))) break;
         if (build_t) rc = build_transpose(g, st);
-        if (rc == 0 && g->nnz > 0) rc = build_ell(g, 0, st);
-        if (rc == 0 && g->nnz > 0 && g->has_t) rc = build_ell(g, 1, st);
     } while (0);
     cudaFree(counts);
     if (rc != 0) {
@@ -409,8 +253,6 @@ int32_t stmgcn_graph_from_csr(stmgcn_graph_t** out, int64_t n, int64_t nnz, cons
         }
         if ((rc = cudaStreamSynchronize(st))) break;
         if (build_t) rc = build_transpose(g, st);
-        if (rc == 0 && g->nnz > 0) rc = build_ell(g, 0, st);
-        if (rc == 0 && g->nnz > 0 && g->has_t) rc = build_ell(g, 1, st);
     } while (0);
     if (rc != 0) {
         free_graph(g);
@@ -456,18 +298,5 @@ void graph_view(const stmgcn_graph* g, bool transpose, int64_t* n, int64_t* nnz,
     *rowptr = transpose ? g->t_rowptr : g->rowptr;
     *colidx = transpose ? g->t_colidx : g->colidx;
     *vals = transpose ? g->t_vals : g->vals;
-}
-}  // namespace stmgcn
-
-namespace stmgcn {
-bool graph_ell_view(const stmgcn_graph* g, bool transpose, int32_t* n_slices, const int32_t** perm, const int32_t** off,
-                    const uint2** ent) {
-    const int o = transpose ? 1 : 0;
-    if (!g->has_ell[o]) return false;
-    *n_slices = g->n_slices;
-    *perm = g->ell_perm[o];
-    *off = g->ell_off[o];
-    *ent = g->ell_ent[o];
-    return true;
 }
 }  // namespace stmgcn

@@ -1,5 +1,7 @@
 // K3b: the shared-weight LSTM of CG_LSTM (reference STMGCN.py:21-22, :44, :47-50; nn.LSTM semantics: gate
-// order i,f,g,o, b_ih + b_hh, zero initial state STMGCN.py:53-57), exact-fp32 CUDA-core path.
+// order i,f,g,o, b_ih + b_hh, zero initial state STMGCN.py:53-57), exact-fp32 CUDA-core path: every shape the
+// tensor-core kernels of lstm16.cu do not cover (H != 64, C > 4), and the on-device reference the parity tests
+// compare those kernels with.  Own tape: hs, cs (L,T,R,H) and post-activation gates (L,T,R,4H), fp32 row-major.
 //
 // Rows r = n*B + b (node-major) so the top layer's last hidden state IS the (N,B,H) operand of the spatial
 // Chebyshev GCN (STMGCN.py:114) with no permute.  The context-gate modulation obs * s[b,t] (STMGCN.py:44)
@@ -11,19 +13,6 @@
 
 using namespace stmgcn;
 
-namespace stmgcn {
-int32_t launch_lstm_cell_tc(const float* seg0, const float* seg1, int nseg, int aux, const float* wimg, const float* bias,
-                            const float* xo, const float* sg, int c_in, int t, int t_len, int64_t b_inner,
-                            const float* c_prev, float* h_out, float* c_out, float* gates_out, int64_t rows,
-                            int blocked_cs, cudaStream_t st);
-int32_t launch_lstm_bwd_tc(int kd, float* gates, const float* c_t, const float* c_prev, const float* dh_in,
-                           float* dh_rec, float* dc, float* dx_out, const float* wimg_t, float* dbp, const float* wx,
-                           float* dwx, const float* xo, const float* sg, float* d_s, int c_in, int t, int t_len,
-                           int64_t b_inner, int64_t rows, int blocked, cudaStream_t st);
-int lstm_tc_max_c_bwd();
-int32_t launch_lstm_wgrad_tc(const float* seg0, const float* seg1, const float* h0, const float* da, float* dwp, int kd,
-                             int t_len, int64_t rows, cudaStream_t st);
-}
 
 namespace {
 
@@ -264,18 +253,16 @@ extern "C" {
 int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
                              const float* wx, const float* const* wp, const float* const* bp,
-                             const float* const* wimg, const float* h0, const float* c0, float* hs, float* cs,
-                             float* gates, int32_t blocked_cs, void* stream) {
+                             const float* h0, const float* c0, float* hs, float* cs, float* gates, void* stream) {
     STMGCN_REQUIRE(xo && s_gate && wx && wp && bp && hs && cs, STMGCN_ERR_ARG, "lstm_step_fwd: null pointer");
     if (int32_t rc = check_dims("lstm_step_fwd", t, t_len, n_layers, rows, hid, c_in, b_inner)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t rh = rows * hid;
-    const int64_t crh = blocked_cs ? ceil_div(rows, 128) * 128 * hid : rh;     // cs / c0 slice size (padded when blocked)
     const int h4 = 4 * hid;
     for (int l = 0; l < n_layers; ++l) {
         STMGCN_REQUIRE(wp[l] && bp[l], STMGCN_ERR_ARG, "lstm_step_fwd: wp/bp[%d] null", l);
         const float* h_prev = t > 0 ? hs + ((int64_t)(l * t_len + t - 1)) * rh : (h0 ? h0 + (int64_t)l * rh : nullptr);
-        const float* c_prev = t > 0 ? cs + ((int64_t)(l * t_len + t - 1)) * crh : (c0 ? c0 + (int64_t)l * crh : nullptr);
+        const float* c_prev = t > 0 ? cs + ((int64_t)(l * t_len + t - 1)) * rh : (c0 ? c0 + (int64_t)l * rh : nullptr);
         ASegs a{};
         a.segw = hid;
         a.lda = hid;
@@ -298,24 +285,12 @@ int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
         epi.b_inner = b_inner;
         epi.c_prev = c_prev;
         epi.h_out = hs + ((int64_t)(l * t_len + t)) * rh;
-        epi.c_out = cs + ((int64_t)(l * t_len + t)) * crh;
+        epi.c_out = cs + ((int64_t)(l * t_len + t)) * rh;
         epi.gates_out = gates ? gates + ((int64_t)(l * t_len + t)) * rows * h4 : nullptr;
         epi.hid = hid;
         epi.half_units = 256 / 8;
         const int kd = a.nseg * hid;
         int32_t rc;
-        const bool tc_ok = wimg && wimg[l] && hid == 64 && aligned16(epi.h_out) && aligned16(epi.c_out) &&
-                           (!epi.gates_out || aligned16(epi.gates_out)) && (!c_prev || aligned16(c_prev)) &&
-                           (!a.seg[0] || aligned16(a.seg[0])) && (a.nseg < 2 || !a.seg[1] || aligned16(a.seg[1]));
-        if (tc_ok) {   // tcgen05 3xTF32 path (lstm_tc.cu)
-            rc = launch_lstm_cell_tc(a.seg[0], a.nseg > 1 ? a.seg[1] : nullptr, a.nseg, l == 0 ? 1 : 0, wimg[l], bp[l], xo,
-                                     s_gate, c_in, t, t_len, b_inner, c_prev, epi.h_out, epi.c_out, epi.gates_out,
-                                     rows, blocked_cs, st);
-            if (rc) return rc;
-            continue;
-        }
-        STMGCN_REQUIRE(!blocked_cs, STMGCN_ERR_STATE,
-                       "lstm_step_fwd: a tile-blocked cell-state tape needs the tensor-core kernel on every layer (layer %d)", l);
         if (vec_ok(a, wp[l], h4, h4))
             rc = launch_tall<256, true>(a, rows, kd, wp[l], h4, h4, epi, st, "lstm_step_fwd");
         else
@@ -327,38 +302,23 @@ int32_t stmgcn_lstm_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
 
 int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
                              int32_t c_in, int64_t b_inner, const float* xo, const float* s_gate,
-                             const float* wx, const float* const* wpt, const float* const* wimg_t,
-                             const float* c0, const float* cs, float* gates, const float* d_top, float* dh_rec,
-                             float* dc, float* dx_work, float* d_s, float* dwx, float* const* dbp, int32_t blocked_ws,
-                             void* stream) {
+                             const float* wx, const float* const* wpt, const float* c0, const float* cs, float* gates,
+                             const float* d_top, float* dh_rec, float* dc, float* dx_work, float* d_s, float* dwx,
+                             float* const* dbp, void* stream) {
     STMGCN_REQUIRE(xo && s_gate && wx && wpt && cs && gates && dh_rec && dc && dx_work && d_s && dwx && dbp,
                    STMGCN_ERR_ARG, "lstm_step_bwd: null pointer");
     if (int32_t rc = check_dims("lstm_step_bwd", t, t_len, n_layers, rows, hid, c_in, b_inner)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t rh = rows * hid;
     const int h4 = 4 * hid;
-    // workspaces dh_rec / dc hold ceil(rows/128)*128 rows per layer when tile-blocked (tensor-core kernels only)
-    const int64_t ws_rh = blocked_ws ? ceil_div(rows, 128) * 128 * hid : rh;
     const int grid_pw = (int)((ceil_div(rows, 8) < (int64_t)sm_count() * 4) ? ceil_div(rows, 8) : (int64_t)sm_count() * 4);
     for (int l = n_layers - 1; l >= 0; --l) {
         STMGCN_REQUIRE(wpt[l] && dbp[l], STMGCN_ERR_ARG, "lstm_step_bwd: wpt/dbp[%d] null", l);
         float* g_lt = gates + ((int64_t)(l * t_len + t)) * rows * h4;
-        const float* c_t = cs + ((int64_t)(l * t_len + t)) * ws_rh;
-        const float* c_prev = t > 0 ? cs + ((int64_t)(l * t_len + t - 1)) * ws_rh : (c0 ? c0 + (int64_t)l * ws_rh : nullptr);
+        const float* c_t = cs + ((int64_t)(l * t_len + t)) * rh;
+        const float* c_prev = t > 0 ? cs + ((int64_t)(l * t_len + t - 1)) * rh : (c0 ? c0 + (int64_t)l * rh : nullptr);
         const float* dh_in = (l == n_layers - 1) ? ((t == t_len - 1) ? d_top : nullptr) : dx_work;
         const bool l0 = (l == 0);
-        if (wimg_t && wimg_t[l] && hid == 64 && (!l0 || c_in <= lstm_tc_max_c_bwd()) && aligned16(g_lt)) {
-            // tcgen05 path: pointwise + data GEMM fused in one kernel (lstm_tc.cu)
-            int32_t rc = launch_lstm_bwd_tc(l0 ? 64 : 128, g_lt, c_t, c_prev, dh_in, dh_rec + (int64_t)l * ws_rh,
-                                            dc + (int64_t)l * ws_rh, l0 ? nullptr : dx_work, wimg_t[l], dbp[l],
-                                            l0 ? wx : nullptr, l0 ? dwx : nullptr, xo, s_gate, d_s, c_in, t, t_len,
-                                            b_inner, rows, blocked_ws, st);
-            if (rc) return rc;
-            continue;
-        }
-        STMGCN_REQUIRE(!blocked_ws, STMGCN_ERR_STATE,
-                       "lstm_step_bwd: tile-blocked workspaces need the tensor-core kernels on every layer (layer %d falls "
-                       "back to the FFMA kernels)", l);
         size_t smem = (size_t)h4 * (1 + (l0 ? c_in : 0)) * sizeof(float);
         if (l0 && b_inner <= 2048) smem += (size_t)b_inner * sizeof(float);
         lstm_bwd_pointwise_kernel<<<grid_pw, 256, smem, st>>>(
@@ -395,8 +355,7 @@ int32_t stmgcn_lstm_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t
 }
 
 int32_t stmgcn_lstm_wgrad(int32_t layer, int32_t t_len, int32_t n_layers, int64_t rows, int32_t hid,
-                          const float* h0, const float* hs, const float* gates_da, float* dwp,
-                          int32_t use_tc, void* stream) {
+                          const float* h0, const float* hs, const float* gates_da, float* dwp, void* stream) {
     STMGCN_REQUIRE(hs && gates_da && dwp, STMGCN_ERR_ARG, "lstm_wgrad: null pointer");
     STMGCN_REQUIRE(layer >= 0 && layer < n_layers && n_layers <= kMaxLayers && t_len > 0 && rows > 0 && hid > 0 &&
                        hid % 4 == 0,
@@ -404,11 +363,6 @@ int32_t stmgcn_lstm_wgrad(int32_t layer, int32_t t_len, int32_t n_layers, int64_
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t rh = rows * hid;
     const int h4 = 4 * hid;
-    if (use_tc && hid == 64 && aligned16(hs) && aligned16(gates_da) && (!h0 || aligned16(h0)))
-        return launch_lstm_wgrad_tc(layer > 0 ? hs + ((int64_t)(layer - 1) * t_len) * rh : nullptr,
-                                    hs + ((int64_t)layer * t_len) * rh, h0 ? h0 + (int64_t)layer * rh : nullptr,
-                                    gates_da + ((int64_t)layer * t_len) * rows * h4, dwp, layer > 0 ? 128 : 64, t_len,
-                                    rows, st);
     ASegs a{};
     ReduceTime tm{};
     a.segw = hid;

@@ -429,7 +429,8 @@ constexpr int kBSgMax = 1024;
 struct B16Tail {
     float bias[kGateCols];
     float wih[kMaxC * kGateCols];
-    float s_db[kBCompWarps][kGateCols];        // per-compute-warp private bias-gradient partial sums (plain adds, no atomics)
+    float s_db[4][kGateCols];                  // bias-gradient partial sums per TMEM lane quadrant: the four warps of a
+                                               // quadrant own disjoint 16-column groups of every chunk (plain adds, no atomics)
     float s_ds[kBSgMax];
     uint64_t a_full, a_empty;
     uint64_t w_full[kBWStages], w_empty[kBWStages];
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     }
     if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, 512);
     for (int i = tid; i < kGateCols; i += kBThreads) tail->bias[i] = p.bias[i] * gate_scale(i);
-    for (int i = tid; i < kBCompWarps * kGateCols; i += kBThreads) (&tail->s_db[0][0])[i] = 0.f;
+    for (int i = tid; i < 4 * kGateCols; i += kBThreads) (&tail->s_db[0][0])[i] = 0.f;
     if (L0) {
         for (int i = tid; i < p.c_in * kGateCols; i += kBThreads) tail->wih[i] = p.wih[i] * gate_scale(i);
         for (int i = tid; i < kBSgMax; i += kBThreads) tail->s_ds[i] = 0.f;
@@ -762,7 +763,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         const int gstep = (int)gridDim.x;
         int tile = (int)blockIdx.x;
         load_raw(tile, 0, nxt);
-        float* my_db = tail->s_db[warp];           // this warp's private bias-gradient accumulators (no atomics)
+        float* my_db = tail->s_db[q];              // this quadrant's bias-gradient accumulators (this warp: its own columns)
         for (int i = 0; i < my_tiles; ++i, tile += gstep) {
             const uint32_t r = (uint32_t)tile * kTileM + row_in_tile;
             const bool valid = r < rows32;
@@ -791,8 +792,6 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             }
             for (int c = 0; c < 4; ++c, ++dcount) {
                 cur = nxt;
-                if (c < 3) load_raw(tile, c + 1, nxt);
-                else load_raw(tile + gstep, 0, nxt);
                 uint32_t v[16];
                 if (p.nseg > 0) {
                     const int b = rcount & 1;
@@ -869,6 +868,10 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tail->d_full);
+                // next chunk's inputs: issued AFTER the proxy fence -- fence.proxy.async implies MEMBAR.ALL.CTA, which waits for
+                // every outstanding load of the thread, so a prefetch issued before it is simply waited for at the fence
+                if (c < 3) load_raw(tile, c + 1, nxt);
+                else load_raw(tile + gstep, 0, nxt);
                 if (valid)
                     *reinterpret_cast<float4*>(p.dc + ((uint32_t)tile * 8192u + (uint32_t)c * 2048u + thr_off)) =
                         make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
@@ -956,7 +959,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     for (int i = tid; i < kGateCols; i += kBThreads) {
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < kBCompWarps; ++w) v += tail->s_db[w][i];
+        for (int w = 0; w < 4; ++w) v += tail->s_db[w][i];
         atomicAdd(&p.dbp[i], v);
     }
     if (L0 && p.b_inner <= kBSgMax)

@@ -9,7 +9,7 @@ Functions (reference lines they replace):
   ChebGCN          GCN.py:24-43 on a sparse L~ (recurrence on features) -> out (N,B,q)
   TemporalPool     STMGCN.py:40-42: GCN over time-as-features + residual + sum over regions -> (B,T)
   ContextGate      STMGCN.py:42-43: /N, fc, relu, fc (same weights), sigmoid -> s (B,T)
-  SharedLSTM       STMGCN.py:44,47-50: modulate + 3-layer shared LSTM, one library call per timestep
+  SharedLSTM       STMGCN.py:44,47-50: modulate + 3-layer shared LSTM, one library call per timestep (lstm16.cu / lstm.cu)
   FuseOut          STMGCN.py:116-118: sum over graphs + output FC -> (B,N,C)
 """
 from __future__ import annotations
@@ -34,7 +34,7 @@ _LSTM_PATH = os.environ.get("STMGCN_LSTM_PATH", "tc")
 
 
 def lstm_path() -> str:
-    """"tc": tcgen05 3xTF32 tensor-core kernels where shapes allow (H = 64); "fma": exact-fp32 FFMA kernels."""
+    """"tc": tcgen05 kernels where shapes allow (LSTM: H = 64, C <= 4; projection: p = q = 64); "fma": exact-fp32 FFMA kernels."""
     return _LSTM_PATH
 
 
@@ -465,6 +465,12 @@ class SharedLSTM(torch.autograd.Function):
     forward(xo (N,B,T,C), s (B,T), h0|None, c0|None (L,R,H), n_layers, hid, want_state, *lstm_weights) where
     lstm_weights = [w_ih_l0, w_hh_l0, b_ih_l0, b_hh_l0, w_ih_l1, ...] (nn.LSTM names/shapes).
     Returns (h_top, h_n (L,R,H), c_n (L,R,H)); the last two are not differentiable.
+
+    Two kernel families (include/stmgcn_b200.h):
+    * H = 64, C <= 4 (the reference's configuration, Main.py:62) and ``lstm_path() == "tc"``: the tcgen05 bf16-plane
+      kernels of lstm16.cu -- tape = hidden-state planes + cell state, no gate tape, fused recompute backward;
+    * anything else, or ``lstm_path() == "fma"``: the exact-fp32 CUDA-core kernels of lstm.cu with their own tape
+      (hs, cs, gates); their backward overwrites the gate tape in place, so it can run only once per forward.
     """
 
     @staticmethod
@@ -478,91 +484,56 @@ class SharedLSTM(torch.autograd.Function):
         h0c = _f32c(h0) if h0 is not None else None
         c0c = _f32c(c0) if c0 is not None else None
         need_grad = any(ctx.needs_input_grad)
-        ctx.planes16 = False
-        env16 = os.environ.get("STMGCN_LSTM16", "1")          # "0": first-generation kernels; "fwd": new forward only
-        if hid == 64 and lstm_path() == "tc" and c_in <= 4 and env16 != "0" and not (need_grad and env16 == "fwd"):
-            # second-generation kernels: bf16 hi/lo planes, resident weights, no gate tape (lstm16.cu)
+        ctx.dims = (n, b, t_len, c_in, n_layers, hid)
+        if hid == 64 and lstm_path() == "tc" and c_in <= 4:
             planes = lstm_planes()
             h_top, h_n, c_n, tape = _lstm16_forward(xo, s_gate, h0c, c0c, n_layers, want_state, weights, planes, need_grad)
             ctx.mark_non_differentiable(h_n, c_n)
+            ctx.planes16 = True
             if need_grad:
-                ctx.planes16, ctx.tape16, ctx.planes = True, tape, planes
-                ctx.dims = (n, b, t_len, c_in, n_layers, hid)
+                ctx.tape16, ctx.planes = tape, planes
                 ctx.save_for_backward(xo, s_gate)
             return h_top, h_n, c_n
+        ctx.planes16 = False
         wx, wp, bp, wpt = _pack_lstm(weights, n_layers, hid)
-        # tensor-core kernels on every layer (H = 64, input_dim = 1): the cell-state tape and the backward workspaces are
-        # tile-blocked so every 8-unit slice of a 128-row tile is one contiguous 4 KB run (see stmgcn_lstm_step_bwd)
-        blocked = bool(hid == 64 and lstm_path() == "tc" and c_in == 1 and os.environ.get("STMGCN_BLOCKED_WS", "1") != "0")
-        rows_c = ((rows + 127) // 128) * 128 if blocked else rows
-        if blocked and c0c is not None:
-            c0c = to_blocked(c0c)
         hs = torch.empty((n_layers, t_len, rows, hid), device=dev, dtype=torch.float32)
-        cs = torch.empty((n_layers, t_len, rows_c, hid), device=dev, dtype=torch.float32)
+        cs = torch.empty((n_layers, t_len, rows, hid), device=dev, dtype=torch.float32)
         gates = torch.empty((n_layers, t_len, rows, 4 * hid), device=dev, dtype=torch.float32) if need_grad else None
         wp_arr, bp_arr = _lib.ptr_array([w.data_ptr() for w in wp]), _lib.ptr_array([v.data_ptr() for v in bp])
         st = _stream()
-        wimg, wimg_t, wimg_arr = None, None, None
-        if hid == 64 and lstm_path() == "tc":           # tcgen05 3xTF32 path: pre-swizzled hi/lo weight images
-            # layer 0 forward operand is augmented: [W_hh^T ; W_ih^T ; bias ; 0] (96 rows) -- x.W_ih + b runs on the MMA
-            aug = torch.zeros((96, 4 * hid), device=dev, dtype=torch.float32)
-            aug[:hid] = wp[0]
-            aug[hid:hid + c_in] = wx
-            aug[hid + c_in] = bp[0]
-            wfwd = [aug] + list(wp[1:])
-            wimg = [torch.empty(w.shape[0] * 4 * hid * 2, device=dev, dtype=torch.float32) for w in wfwd]
-            wimg_t = [torch.empty(w.shape[0] * 4 * hid * 2, device=dev, dtype=torch.float32) if need_grad else None
-                      for w in wp]
-            for wf, wb, img, img_t in zip(wfwd, wp, wimg, wimg_t):
-                _lib.check(L.stmgcn_lstm_pack_tc(wf.data_ptr(), wf.shape[0], wb.data_ptr(), wb.shape[0], hid,
-                                                 img.data_ptr(), _p(img_t), st), "lstm_pack_tc")
-            wimg_arr = _lib.ptr_array([v.data_ptr() for v in wimg])
         for t in range(t_len):
             _lib.check(L.stmgcn_lstm_step_fwd(t, t_len, n_layers, rows, hid, c_in, b, xo.data_ptr(),
-                                              s_gate.data_ptr(), wx.data_ptr(), wp_arr, bp_arr, wimg_arr, _p(h0c),
-                                              _p(c0c), hs.data_ptr(), cs.data_ptr(), _p(gates), int(blocked), st),
-                       "lstm_step_fwd")
-        ctx.dims = (n, b, t_len, c_in, n_layers, hid)
-        ctx.tc = wimg is not None
-        ctx.blocked = blocked
+                                              s_gate.data_ptr(), wx.data_ptr(), wp_arr, bp_arr, _p(h0c), _p(c0c),
+                                              hs.data_ptr(), cs.data_ptr(), _p(gates), st), "lstm_step_fwd")
         if need_grad:
-            ctx.save_for_backward(xo, s_gate, h0c, c0c, hs, cs, gates, wx, *wpt, *(wimg_t if ctx.tc else []))
+            ctx.save_for_backward(xo, s_gate, h0c, c0c, hs, cs, gates, wx, *wpt)
         h_top = hs[n_layers - 1, t_len - 1].view(n, b, hid)
         if want_state:
-            h_n = hs[:, t_len - 1]
-            c_n = from_blocked(cs[:, t_len - 1], rows) if blocked else cs[:, t_len - 1]
-        else:                       # ST_MGCN discards the final state (STMGCN.py:113): skip the layout conversion
+            h_n, c_n = hs[:, t_len - 1], cs[:, t_len - 1]
+        else:                       # ST_MGCN discards the final state (STMGCN.py:113)
             h_n = c_n = hs.new_empty(0)
         ctx.mark_non_differentiable(h_n, c_n)
         return h_top, h_n, c_n
 
     @staticmethod
     def backward(ctx, d_top, _dhn, _dcn):
+        n, b, t_len, c_in, n_layers, hid = ctx.dims
         if ctx.planes16:
             xo, s_gate = ctx.saved_tensors
-            d_s, w_grads = _lstm16_backward(xo, s_gate, ctx.tape16, ctx.dims[4], ctx.planes, d_top)
+            d_s, w_grads = _lstm16_backward(xo, s_gate, ctx.tape16, n_layers, ctx.planes, d_top)
             return (None, d_s, None, None, None, None, None, *w_grads)
         if getattr(ctx, "tape_consumed", False):
-            raise RuntimeError("SharedLSTM (first-generation kernels): the gate tape was overwritten in place by the first "
-                               "backward pass; a second backward over the same graph is not supported")
+            raise RuntimeError("SharedLSTM (exact-fp32 kernels): the gate tape was overwritten in place by the first backward "
+                               "pass; a second backward over the same graph is not supported on this path")
         ctx.tape_consumed = True
-        xo, s_gate, h0, c0, hs, cs, gates, wx, *rest = ctx.saved_tensors
-        n, b, t_len, c_in, n_layers, hid = ctx.dims
-        wpt, wimg_t = rest[:n_layers], rest[n_layers:]
-        wimg_t_arr = _lib.ptr_array([v.data_ptr() for v in wimg_t]) if ctx.tc else None
+        xo, s_gate, h0, c0, hs, cs, gates, wx, *wpt = ctx.saved_tensors
         rows = n * b
         dev = xo.device
         d_top = _f32c(d_top).view(rows, hid)
-        # tensor-core kernels on every layer (input_dim == 1): tile-blocked workspaces, every 8-unit slice of a 128-row
-        # tile is one contiguous 4 KB run (full-line loads/stores instead of 32-byte pieces at a 256-byte stride)
-        blocked = ctx.blocked
-        rows_ws = ((rows + 127) // 128) * 128 if blocked else rows
-        if blocked:
-            d_top = to_blocked(d_top)
         # dh_rec / dc need no initialisation: the step at t = T-1 treats them as zero (stmgcn_lstm_step_bwd)
-        dh_rec = torch.empty((n_layers, rows_ws, hid), device=dev, dtype=torch.float32)
-        dc = torch.empty((n_layers, rows_ws, hid), device=dev, dtype=torch.float32)
-        dx_work = torch.empty((rows_ws, hid), device=dev, dtype=torch.float32)
+        dh_rec = torch.empty((n_layers, rows, hid), device=dev, dtype=torch.float32)
+        dc = torch.empty((n_layers, rows, hid), device=dev, dtype=torch.float32)
+        dx_work = torch.empty((rows, hid), device=dev, dtype=torch.float32)
         d_s = torch.zeros((b, t_len), device=dev, dtype=torch.float32)
         dwx = torch.zeros_like(wx)
         dbp = [torch.zeros(4 * hid, device=dev, dtype=torch.float32) for _ in range(n_layers)]
@@ -570,16 +541,16 @@ class SharedLSTM(torch.autograd.Function):
         wpt_arr = _lib.ptr_array([w.data_ptr() for w in wpt])
         dbp_arr = _lib.ptr_array([v.data_ptr() for v in dbp])
         st = _stream()
-        # NOTE: gates is overwritten in place with dA (the tape is consumed; double backward unsupported)
+        # NOTE: gates is overwritten in place with dA (the tape is consumed; see the guard above)
         for t in range(t_len - 1, -1, -1):
             _lib.check(L.stmgcn_lstm_step_bwd(t, t_len, n_layers, rows, hid, c_in, b, xo.data_ptr(),
-                                              s_gate.data_ptr(), wx.data_ptr(), wpt_arr, wimg_t_arr, _p(c0), cs.data_ptr(),
+                                              s_gate.data_ptr(), wx.data_ptr(), wpt_arr, _p(c0), cs.data_ptr(),
                                               gates.data_ptr(), d_top.data_ptr(), dh_rec.data_ptr(),
                                               dc.data_ptr(), dx_work.data_ptr(), d_s.data_ptr(), dwx.data_ptr(),
-                                              dbp_arr, int(blocked), st), "lstm_step_bwd")
+                                              dbp_arr, st), "lstm_step_bwd")
         for l in range(n_layers):
             _lib.check(L.stmgcn_lstm_wgrad(l, t_len, n_layers, rows, hid, _p(h0), hs.data_ptr(), gates.data_ptr(),
-                                           dwp[l].data_ptr(), int(ctx.tc), st), "lstm_wgrad")
+                                           dwp[l].data_ptr(), st), "lstm_wgrad")
         w_grads = _unpack_lstm_grads(dwx, dwp, dbp, n_layers, hid, c_in)
         return (None, d_s, None, None, None, None, None, *w_grads)
 

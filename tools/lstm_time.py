@@ -1,5 +1,5 @@
 """Time the shared LSTM of one graph branch alone (cfg3 rows) -- forward (no_grad) and forward+backward -- on the current
-kernels.  Usage: python tools/lstm_time.py [rows_n] [batch] [T]    (env STMGCN_LSTM16=0 selects the first-generation kernels)"""
+kernels.  Usage: python tools/lstm_time.py [rows_n] [batch] [T]    (env STMGCN_LSTM_PATH=fma selects the exact-fp32 CUDA-core kernels)"""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "st-mgcn_b200")]
@@ -44,6 +44,6 @@ def fwd_bwd():
     h, _, _ = ops.SharedLSTM.apply(xo, sr, None, None, lyr, hid, False, *wr)
     h.backward(d_top)
 
-out = {"rows": n * b, "T": t, "lstm16": os.environ.get("STMGCN_LSTM16", "1"), "planes": ops.lstm_planes(),
+out = {"rows": n * b, "T": t, "path": ops.lstm_path(), "planes": ops.lstm_planes(),
        "fwd_ms": timed(fwd_only), "fwd_bwd_ms": timed(fwd_bwd)}
 print(json.dumps(out))
