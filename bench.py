@@ -473,14 +473,28 @@ def run_ours(args, w):
             achieved = (sum(alg_dom) * (k_ord - 1)) / (ms_dom * 1e-3) / 1e9
         else:
             us_launch, achieved = ms_spmm * 1e3 / max(n_launch, 1), alg / (ms_spmm * 1e-3) / 1e9
-        # DRAM bytes per launch of this launch type from the committed ncu --set full capture (profiles/): only valid
-        # for the exact shape it was captured on (cfg3, batch 64)
-        traffic = 183.4e6 if (w.name == "cfg3" and b == 64) else None
+        # DRAM bytes per launch of this launch type: read from the committed summary of this round's `ncu --set full`
+        # capture of exactly this launch (tools/ncu_spmm.sh -> tools/ncu_summary.py -> profiles/r2_spmm_ncu.json); only
+        # valid for the shape it was captured on (cfg3, batch 64)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(REPO, "profiles", "r2_spmm_ncu.json")
+        if w.name == "cfg3" and b == 64 and os.path.exists(tpath):
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            try:
+                mb = float(tj["dram__bytes_read.sum"]) + float(tj["dram__bytes_write.sum"])
+                traffic = mb * 1e6
+                traffic_src = ("profiles/r2_spmm_ncu.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch "
+                               f"({tj['dram__bytes_read.sum']} + {tj['dram__bytes_write.sum']} MB), ncu --set full")
+            except (KeyError, ValueError):
+                pass
         roofline = {"bound": "hbm", "kernel": "spmm_row_gather_kernel<4> (Chebyshev recurrence step, spatial, k>=2)",
                     "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": f"{pk_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                    "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
-                    "traffic_source": "profiles/r1_spmm_v1_ncu_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum, "
-                                      "per launch (136.0 + 47.4 MB)" if traffic else None,
+                    "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                    "gather_ceiling": {"measured_gather_GBps": 17900, "source": "profiles/r2_gather_probe.log (tools/gather_probe.cu: "
+                                       "512-byte row-segment gathers through L2/L1, same N / F / degree)",
+                                       "note": "the launch gathers nnz*F*4 B = 2.87 GB against 0.2 GB of algorithmic HBM bytes; "
+                                               "at the measured gather rate that alone is 160 us"},
                     "algorithmic_bytes_per_launch": sum(alg_dom) / len(alg_dom), "avg_us_per_launch": us_launch,
                     "launches_timed": n_dom,
                     "forward_all": {"algorithmic_bytes": alg, "launches": n_launch, "ms": ms_spmm,

@@ -16,6 +16,7 @@ int32_t fail(int32_t code, const char* fmt, ...);
 int32_t check_launch(const char* what);        // cudaGetLastError() only -- never synchronises
 void count_launch(int n = 1);
 int sm_count();
+int32_t ensure_dyn_smem(const void* kernel, size_t bytes);   // per-(kernel, device) cudaFuncAttributeMaxDynamicSharedMemorySize
 
 #define STMGCN_REQUIRE(cond, code, ...)                                   \
     do {                                                                  \

@@ -2,6 +2,7 @@
 // supports; the hot path keeps supports[1] -- the rescaled Laplacian -- as CSR and CSR^T on the device).
 // One-time setup code: cub (CUDA toolkit, header-only) is used for the scans and the transpose sort.
 #include "common.cuh"
+#include <mutex>
 
 #include <cub/cub.cuh>
 #include <atomic>
@@ -42,6 +43,29 @@ int sm_count() {
         cached[dev] = v;
     }
     return cached[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember (kernel, device) pairs, not a
+// process-wide flag, so a model moved to another GPU of the same process still launches; mutex: the forward
+// thread and the autograd thread may both get here first.
+int32_t ensure_dyn_smem(const void* kernel, size_t bytes) {
+    constexpr int kMaxKernels = 32, kMaxDev = 64;
+    static std::mutex mu;
+    static const void* kernels[kMaxKernels] = {};
+    static bool done[kMaxKernels][kMaxDev] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+    std::lock_guard<std::mutex> lock(mu);
+    int slot = -1;
+    for (int i = 0; i < kMaxKernels; ++i) {
+        if (kernels[i] == kernel) { slot = i; break; }
+        if (kernels[i] == nullptr) { kernels[i] = kernel; slot = i; break; }
+    }
+    if (slot >= 0 && dev >= 0 && dev < kMaxDev && done[slot][dev]) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail((int32_t)e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s", bytes, cudaGetErrorString(e));
+    if (slot >= 0 && dev >= 0 && dev < kMaxDev) done[slot][dev] = true;
+    return 0;
 }
 
 }  // namespace stmgcn

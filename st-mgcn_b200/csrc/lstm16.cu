@@ -129,7 +129,7 @@ struct Fwd16Params {
     int n_tiles;
 };
 
-template <int PLANES>
+template <int PLANES, bool L0>
 __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_constant__ Fwd16Params p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would make every access through
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
     }
     if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, 512);
     for (int i = tid; i < kGateCols; i += kFThreads) tail->bias[i] = p.bias[i] * gate_scale(i);
-    if (p.wih != nullptr)
+    if (L0)
         for (int i = tid; i < p.c_in * kGateCols; i += kFThreads) tail->wih[i] = p.wih[i] * gate_scale(i);
     tc_fence_before();
     __syncthreads();
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
         // TMEM lane quadrant q = warp & 3 (rows 32q .. 32q+31 of the tile), column quarter part = warp >> 2
         // (gate columns 64*part .. +63 = units 16*part .. +15), four pieces of 16 columns = 4 units each
         const int q = warp & 3, part = warp >> 2;
-        const bool l0 = p.wih != nullptr;
+        constexpr bool l0 = L0;
         // c_{t-1} of this thread's row (16 units) lives in registers; the four floats a piece has just consumed are
         // reloaded at once with the NEXT tile's values, so the loads are in flight for most of a tile (loading all 16 at the
         // end of a tile exposed the full DRAM latency at the top of the next one: ncu showed 21 % of the samples there)
@@ -298,6 +298,8 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                 tc_fence_after();
             }
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * kGateCols + (uint32_t)part * 64;
+            // (measured and rejected: software-pipelining the tcgen05.ld of the next piece under this piece's arithmetic with
+            //  per-piece 8-byte h stores -- 3.77 ms per branch forward against 2.86 ms for this load-then-wait form)
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int pc = 0; pc < 4; ++pc) {
@@ -1028,23 +1030,7 @@ bool make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int64_t sl
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int32_t set_smem_attr(const void* fn, size_t bytes) {
-    // per device (the attribute is per device): cheap, so set unconditionally per launch site on first use per device
-    static bool done[64][8] = {};
-    static const void* fns[8] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    int slot = -1;
-    for (int i = 0; i < 8; ++i) {
-        if (fns[i] == fn) { slot = i; break; }
-        if (fns[i] == nullptr) { fns[i] = fn; slot = i; break; }
-    }
-    if (slot < 0 || dev < 0 || dev >= 64 || !done[dev][slot]) {
-        STMGCN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        if (slot >= 0 && dev >= 0 && dev < 64) done[dev][slot] = true;
-    }
-    return 0;
-}
+static int32_t set_smem_attr(const void* fn, size_t bytes) { return ensure_dyn_smem(fn, bytes); }
 
 }  // namespace stmgcn
 
@@ -1074,7 +1060,8 @@ extern "C" int32_t stmgcn_lstm16_step_fwd(int32_t t, int32_t t_len, int32_t n_la
     const int64_t rows_pad = (int64_t)n_tiles * kTileM;
     const int64_t plane_elems = rows * kHid;                       // bf16 elements per plane
     const int64_t cslice = rows_pad * kHid;
-    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_fwd_kernel<2> : (const void*)lstm16_fwd_kernel<1>, kFSmem)) return rc;
+    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_fwd_kernel<2, true> : (const void*)lstm16_fwd_kernel<1, true>, kFSmem)) return rc;
+    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_fwd_kernel<2, false> : (const void*)lstm16_fwd_kernel<1, false>, kFSmem)) return rc;
     CUtensorMap hp_map, h0_map;
     STMGCN_REQUIRE(make_plane_map(&hp_map, hp, rows, (int64_t)n_layers * t_len * planes), STMGCN_ERR_STATE,
                    "lstm16_step_fwd: cuTensorMapEncodeTiled failed (hp)");
@@ -1125,8 +1112,13 @@ extern "C" int32_t stmgcn_lstm16_step_fwd(int32_t t, int32_t t_len, int32_t n_la
         }
         p.rows = rows;
         p.n_tiles = n_tiles;
-        if (planes == 2) lstm16_fwd_kernel<2><<<grid, kFThreads, kFSmem, st>>>(p);
-        else lstm16_fwd_kernel<1><<<grid, kFThreads, kFSmem, st>>>(p);
+        if (planes == 2) {
+            if (l == 0) lstm16_fwd_kernel<2, true><<<grid, kFThreads, kFSmem, st>>>(p);
+            else lstm16_fwd_kernel<2, false><<<grid, kFThreads, kFSmem, st>>>(p);
+        } else {
+            if (l == 0) lstm16_fwd_kernel<1, true><<<grid, kFThreads, kFSmem, st>>>(p);
+            else lstm16_fwd_kernel<1, false><<<grid, kFThreads, kFSmem, st>>>(p);
+        }
         count_launch();
         if (int32_t rc = check_launch("lstm16_fwd")) return rc;
     }

@@ -228,12 +228,8 @@ bool proj_tc_applicable(int ks, int p, int q, const void* a, const void* b, cons
 // forward: out = act(sum_k S_k W_k + bias); wimg = image of B[n][k] = W[k][n] (2*ks k-blocks of [hi|lo] [64][32])
 int32_t launch_proj_fwd_tc(const float* s, int64_t stride_k, int ks, int64_t rows, const float* wimg, const float* bias,
                            int act, float* out, cudaStream_t st) {
-    static bool attr_done = false;
     auto kern = proj_rows_tc_kernel<64, false>;
-    if (!attr_done) {
-        STMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem<64>()));
-        attr_done = true;
-    }
+    if (int32_t rc = ensure_dyn_smem((const void*)kern, psmem<64>())) return rc;
     PParams p{};
     for (int k = 0; k < ks; ++k) p.seg[k] = s + (int64_t)k * stride_k;
     p.nkb = 2 * ks;
@@ -253,12 +249,8 @@ int32_t launch_proj_fwd_tc(const float* s, int64_t stride_k, int ks, int64_t row
 // wimg_t = image of B[n = k*64+i][k' = j] = W[n][j]  (2 k-blocks of [hi|lo] [ks*64][32])
 int32_t launch_proj_bwd_tc(const float* d_out, const float* out_act, int act, int64_t rows, int ks, const float* wimg_t,
                            float* dz_out, float* dbias, float* u, int64_t stride_u, cudaStream_t st) {
-    static bool attr_done = false;
     auto kern = proj_rows_tc_kernel<256, true>;
-    if (!attr_done) {
-        STMGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem<256>()));
-        attr_done = true;
-    }
+    if (int32_t rc = ensure_dyn_smem((const void*)kern, psmem<256>())) return rc;
     PParams p{};
     p.nkb = 2;
     p.ks_out = ks;

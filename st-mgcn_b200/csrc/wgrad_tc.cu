@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
 
 namespace stmgcn {
 
-// Weight-gradient reduction on the tensor cores.  LSTM (n = 256, shift1 = 1): called from stmgcn_lstm_wgrad;
-// projection (n = 64, shift1 = 0, t_len = 1): called from stmgcn_proj_bwd, once per 128-row block of dW.
+// Weight-gradient reduction on the tensor cores for the projection (n = 64, shift1 = 0, t_len = 1): called from
+// stmgcn_proj_bwd, once per 128-row block of dW.
 int32_t launch_wgrad_tc(const float* seg0, const float* seg1, const float* h0, int shift1, const float* da, int n,
                         float* dwp, int kd, int t_len, int64_t rows, cudaStream_t st) {
     WgParams p;
@@ -222,7 +222,7 @@ int32_t launch_wgrad_tc(const float* seg0, const float* seg1, const float* h0, i
     p.total_chunks = p.chunks_per_t * t_len;
     const int64_t grid = p.total_chunks < sm_count() ? p.total_chunks : sm_count();
     STMGCN_REQUIRE(n == 64, STMGCN_ERR_SHAPE, "wgrad_tc: n=%d (only the projection's N = 64 is instantiated)", n);
-    STMGCN_CUDA(cudaFuncSetAttribute(lstm_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgCfg<64>::kSmem));
+    if (int32_t rc = ensure_dyn_smem((const void*)lstm_wgrad_tc_kernel<64>, WgCfg<64>::kSmem)) return rc;
     lstm_wgrad_tc_kernel<64><<<(int)grid, kWgThreads, WgCfg<64>::kSmem, st>>>(p);
     count_launch();
     return check_launch("wgrad_tc");
