@@ -130,13 +130,32 @@ def adjoint_stack_(sset: SupportSet, u: torch.Tensor) -> torch.Tensor:
     return acc
 
 
+_PROJ_CACHE: "OrderedDict" = OrderedDict()
+
+
 def _proj_images(w: torch.Tensor, ks: int, p: int, need_bwd: bool):
-    """tcgen05 operand images of the projection weights (p = q = 64, ks <= 4), or (None, None)."""
+    """tcgen05 operand images of the projection weights (p = q = 64, ks <= 8), or (None, None).  Cached on the
+    parameter's storage + in-place version (re-packed only after an optimizer step; bypassed during CUDA-graph capture so
+    the pack kernels are part of the graph)."""
     if lstm_path() != "tc" or p != 64 or w.shape[1] != 64 or ks > 8:
         return None, None
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (w.data_ptr(), w._version, ks, str(w.device))
+    if not capturing:
+        hit = _PROJ_CACHE.get(key)
+        if hit is not None and (hit[1] is not None or not need_bwd):
+            _PROJ_CACHE.move_to_end(key)
+            torch.cuda.current_stream().wait_event(hit[2])
+            return hit[0], hit[1]
     img_f = torch.empty(ks * 64 * 64 * 2, device=w.device, dtype=torch.float32)
     img_b = torch.zeros((2 if ks > 4 else 1) * 2 * 2 * 256 * 32, device=w.device, dtype=torch.float32) if need_bwd else None
     _lib.check(L.stmgcn_proj_pack_tc(w.data_ptr(), ks, img_f.data_ptr(), _p(img_b), _stream()), "proj_pack_tc")
+    if not capturing:
+        ev = torch.cuda.Event()
+        ev.record()
+        _PROJ_CACHE[key] = (img_f, img_b, ev, w)          # keeps `w` alive: a recycled data_ptr can never alias the key
+        while len(_PROJ_CACHE) > _W16_MAX:
+            _PROJ_CACHE.popitem(last=False)
     return img_f, img_b
 
 
