@@ -423,7 +423,8 @@ __global__ void lstm16_pack_kernel(const float* __restrict__ w_ih, const float* 
 // the slices once per layer and writes nn.LSTM-native gradients.
 constexpr int kBCompWarps = 16;
 constexpr int kBThreads = (kBCompWarps + 4) * 32;       // + three MMA-issuing warps + producer warp
-constexpr int kBWStages = 3;
+constexpr int kBWStages = 2;                            // a weight chunk is held from R_c to D_c: two suffice while the compute
+                                                        // warps, not the tensor pipe, set the pace (a chunk-time >> MMA + reload)
 constexpr int kBWChunkTile = 64 * 128;                  // [64 gate cols][64 k] bf16 = 8 KB
 constexpr int kBWStageBytes = 4 * kBWChunkTile;         // (seg0 hi | seg0 lo | seg1 hi | seg1 lo) = 32 KB
 constexpr int kBSgMax = 1024;
@@ -434,7 +435,8 @@ struct B16Tail {
     float s_db[4][kGateCols];                  // bias-gradient partial sums per TMEM lane quadrant: the four warps of a
                                                // quadrant own disjoint 16-column groups of every chunk (plain adds, no atomics)
     float s_ds[kBSgMax];
-    uint64_t a_full, a_empty;
+    uint64_t ahi_full[2], ahi_empty[2];        // A hi planes: double-buffered by tile parity
+    uint64_t alo_full, alo_empty;              // A lo planes: single buffer
     uint64_t w_full[kBWStages], w_empty[kBWStages];
     uint64_t r_full[2], r_empty[2];
     uint64_t d_full, d_empty;
@@ -442,7 +444,8 @@ struct B16Tail {
     uint64_t done;
     uint32_t tmem_base;
 };
-constexpr size_t kBSmem = 1024 + 4 * (size_t)kATileBytes + (size_t)kBWStages * kBWStageBytes + 2 * (size_t)kATileBytes + sizeof(B16Tail);
+constexpr int kBATiles = 6;                             // hi planes of two tiles (2 x 2 segments) + lo planes of one (2 segments)
+constexpr size_t kBSmem = 1024 + kBATiles * (size_t)kATileBytes + (size_t)kBWStages * kBWStageBytes + 2 * (size_t)kATileBytes + sizeof(B16Tail);
 static_assert(kBSmem <= 232448, "lstm16 backward kernel exceeds the 227 KB shared-memory limit");
 
 struct Bwd16Params {
@@ -479,8 +482,12 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would make every access through
     // `smem` a generic LD/ST/ATOM instead of LDS/STS/ATOMS: ncu showed the bias loads as long-scoreboard stalls)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* a_sm = smem;                                          // tiles 0..3: seg0 hi | seg0 lo | seg1 (aux) hi | seg1 (aux) lo
-    uint8_t* w_sm = a_sm + 4 * (size_t)kATileBytes;                // weight chunk ring
+    // A planes: tiles [hi buffer 0: seg0, seg1 (aux)] [hi buffer 1: seg0, seg1 (aux)] [lo: seg0, seg1 (aux)].  The hi planes
+    // of the NEXT tile load while this tile is processed; the lo planes (needed by one of three passes) are single-buffered
+    // and released by the FIRST pass of the tile's last weight-gradient MMA group.  Fully single-buffered planes cost the
+    // compute warps 16 % of their lifetime waiting for the first recompute of every tile (role accounting, profiles/).
+    uint8_t* a_sm = smem;
+    uint8_t* w_sm = a_sm + kBATiles * (size_t)kATileBytes;         // weight chunk ring
     uint8_t* da_sm = w_sm + (size_t)kBWStages * kBWStageBytes;     // dA chunk: hi tile | lo tile
     B16Tail* tail = (B16Tail*)(da_sm + 2 * (size_t)kATileBytes);
     const int tid = threadIdx.x;
@@ -492,8 +499,12 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     constexpr uint32_t kWgCol = 0, kDgCol = 256, kRcCol = 384;     // TMEM columns: weight grad | data grad | recompute x2
 
     if (tid == 0) {
-        mbar_init(&tail->a_full, 1);
-        mbar_init(&tail->a_empty, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tail->ahi_full[b], 1);
+            mbar_init(&tail->ahi_empty[b], 1);
+        }
+        mbar_init(&tail->alo_full, 1);
+        mbar_init(&tail->alo_empty, 1);
         for (int s = 0; s < kBWStages; ++s) {
             mbar_init(&tail->w_full[s], 1);
             mbar_init(&tail->w_empty[s], 1);
@@ -525,51 +536,74 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     // operand tiles of the weight-gradient GEMM (MN-major view): atom 0 and atom 1 along M = kd
     // layers > 0: atom 0 = h_below, atom 1 = h_prev (absent: duplicate of atom 0, rows 64.. are not flushed)
     // layer 0   : atom 0 = h_prev (absent at t = 0: duplicate of the auxiliary tile), atom 1 = auxiliary [x*s] tile
-    const uint32_t wg_a0 = (L0 && p.nseg == 0) ? 2u : 0u;
-    const uint32_t wg_lbo = (L0 ? (p.nseg == 0 ? 0u : 2u) : (p.nseg == 2 ? 2u : 0u)) * kATileBytes;
+    const uint32_t wg_a0 = (L0 && p.nseg == 0) ? 1u : 0u;          // segment slot of atom 0
+    const uint32_t wg_lbo = (L0 ? (p.nseg == 0 ? 0u : 1u) : (p.nseg == 2 ? 1u : 0u)) * kATileBytes;
 
     if (warp == kProdWarp) {
         // ===================== producer =====================
         TC_PROF_DECL
-        if (lane == 0) {
-            uint32_t wc = 0;
+        if (lane == 0 && p.nseg > 0 && my_tiles > 0) {
+            const int first = (int)blockIdx.x, gstep = (int)gridDim.x;
+            auto load_hi = [&](int i) {                 // hi planes of tile i -> hi buffer i & 1
+                const int b = i & 1;
+                if (i >= 2) mbar_wait_p(&tail->ahi_empty[b], (uint32_t)((i >> 1) - 1) & 1, 1);
+                mbar_arrive_expect_tx(&tail->ahi_full[b], (uint32_t)(p.nseg * kATileBytes));
+                for (int s = 0; s < p.nseg; ++s)
+                    tma_load_3d(a_sm + (size_t)(b * 2 + s) * kATileBytes, &p.amap[s], 0, (first + i * gstep) * kTileM, p.aslice[s],
+                                &tail->ahi_full[b]);
+            };
+            auto load_lo = [&](int i) {                 // lo planes of tile i -> the single lo buffer
+                if (i >= 1) mbar_wait_p(&tail->alo_empty, (uint32_t)(i - 1) & 1, 1);
+                mbar_arrive_expect_tx(&tail->alo_full, (uint32_t)(p.nseg * kATileBytes));
+                for (int s = 0; s < p.nseg; ++s)
+                    tma_load_3d(a_sm + (size_t)(4 + s) * kATileBytes, &p.amap[s], 0, (first + i * gstep) * kTileM, p.aslice[s] + 1,
+                                &tail->alo_full);
+            };
+            auto load_w = [&](uint32_t wc) {            // weight chunk wc & 3 -> ring stage wc % kBWStages
+                const int stg = wc % kBWStages, c = wc & 3;
+                const uint32_t ph = (wc / kBWStages) & 1;
+                mbar_wait_p(&tail->w_empty[stg], ph ^ 1, 0);
+                mbar_arrive_expect_tx(&tail->w_full[stg], (uint32_t)(p.nseg * PLANES * kBWChunkTile));
+                for (int s = 0; s < p.nseg; ++s)
+                    for (int pl = 0; pl < PLANES; ++pl)
+                        bulk_g2s(w_sm + (size_t)stg * kBWStageBytes + (size_t)(s * 2 + pl) * kBWChunkTile,
+                                 p.wimg + (size_t)(s * 2 + pl) * kWTileBytes + (size_t)c * kBWChunkTile, kBWChunkTile, &tail->w_full[stg]);
+            };
+            auto prefetch_next = [&](int i) {           // tile i's lo planes and per-row inputs -> L2
+                const int tile = first + i * gstep;
+                if (PLANES == 2)
+                    for (int s = 0; s < p.nseg; ++s) tma_prefetch_3d(&p.amap[s], 0, tile * kTileM, p.aslice[s] + 1);
+                // the compute warps' per-row inputs (a tile is one contiguous 32 KB run in every workspace): their
+                // one-chunk-ahead register prefetch then costs an L2 hit, not a DRAM round trip
+                const int64_t o = (int64_t)tile * kTileM * kHid;
+                constexpr uint32_t kB = kTileM * kHid * 4;
+                if (p.c_prev) prefetch_l2(p.c_prev + o, kB);
+                if (p.dh_in) prefetch_l2(p.dh_in + o, kB);
+                if (!p.first) {
+                    prefetch_l2(p.dh_rec + o, kB);
+                    prefetch_l2(p.dc + o, kB);
+                }
+            };
+            // Flat schedule.  Every wait below is on an event that lies in the PAST of what the consumers need next, so the
+            // single producer thread never delays a consumer: weight chunk (i+1, 0) is requested as soon as D_2(i) has released
+            // its stage, before the wait for the lo buffer (released by W_3(i)), so the first recompute of tile i+1 is in
+            // flight while the compute warps are still on the last chunk of tile i.
+            load_hi(0);
+            if (PLANES == 2) load_lo(0);
+            load_w(0);
+            load_w(1);
             for (int i = 0; i < my_tiles; ++i) {
-                const int tile = blockIdx.x + i * gridDim.x;
-                if (p.nseg > 0) {
-                    if (i > 0) mbar_wait_p(&tail->a_empty, (uint32_t)(i - 1) & 1, 1);
-                    mbar_arrive_expect_tx(&tail->a_full, (uint32_t)(p.nseg * PLANES * kATileBytes));
-                    for (int s = 0; s < p.nseg; ++s)
-                        for (int pl = 0; pl < PLANES; ++pl)
-                            tma_load_3d(a_sm + (size_t)(s * 2 + pl) * kATileBytes, &p.amap[s], 0, tile * kTileM, p.aslice[s] + pl,
-                                        &tail->a_full);
-                    // the A planes are single-buffered (they stay resident until the tile's last weight-gradient MMA): pull
-                    // the NEXT tile's planes into L2 now so that the exposed part of their load is an L2 hit, not HBM latency
-                    if (i + 1 < my_tiles) {
-                        for (int s = 0; s < p.nseg; ++s)
-                            for (int pl = 0; pl < PLANES; ++pl)
-                                tma_prefetch_3d(&p.amap[s], 0, (tile + (int)gridDim.x) * kTileM, p.aslice[s] + pl);
-                        // ... and the compute warps' per-row inputs (a tile is one contiguous 32 KB run in every workspace):
-                        // their one-chunk-ahead register prefetch then costs an L2 hit, not a DRAM round trip
-                        const int64_t o = (int64_t)(tile + (int)gridDim.x) * kTileM * kHid;
-                        constexpr uint32_t kB = kTileM * kHid * 4;
-                        if (p.c_prev) prefetch_l2(p.c_prev + o, kB);
-                        if (p.dh_in) prefetch_l2(p.dh_in + o, kB);
-                        if (!p.first) {
-                            prefetch_l2(p.dh_rec + o, kB);
-                            prefetch_l2(p.dc + o, kB);
-                        }
-                    }
-                    for (int c = 0; c < 4; ++c, ++wc) {
-                        const int stg = wc % kBWStages;
-                        const uint32_t ph = (wc / kBWStages) & 1;
-                        mbar_wait_p(&tail->w_empty[stg], ph ^ 1, 0);
-                        mbar_arrive_expect_tx(&tail->w_full[stg], (uint32_t)(p.nseg * PLANES * kBWChunkTile));
-                        for (int s = 0; s < p.nseg; ++s)
-                            for (int pl = 0; pl < PLANES; ++pl)
-                                bulk_g2s(w_sm + (size_t)stg * kBWStageBytes + (size_t)(s * 2 + pl) * kBWChunkTile,
-                                         p.wimg + (size_t)(s * 2 + pl) * kWTileBytes + (size_t)c * kBWChunkTile, kBWChunkTile,
-                                         &tail->w_full[stg]);
-                    }
+                const bool more = i + 1 < my_tiles;
+                if (more) {
+                    load_hi(i + 1);
+                    prefetch_next(i + 1);
+                }
+                load_w((uint32_t)(4 * i + 2));
+                load_w((uint32_t)(4 * i + 3));
+                if (more) {
+                    load_w((uint32_t)(4 * i + 4));
+                    if (PLANES == 2) load_lo(i + 1);
+                    load_w((uint32_t)(4 * i + 5));
                 }
             }
         }
@@ -595,13 +629,14 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         const int role = warp - kMmaWarp;                                  // 0: R, 1: W, 2: D
         if (role == 0) {
             // ---- R: G_c[128 x 64] = [h_below | h_prev] . Wp[:, chunk c]  into one of two TMEM buffers ----
-            const uint64_t rc_a = desc16_k(a_u);                           // + (s*2 + plane) * kTileEnc
+            const uint64_t rc_a = desc16_k(a_u);                           // hi: + (buffer*2 + s) * kTileEnc; lo: + (4 + s) * kTileEnc
             const uint64_t rc_b = desc16_k(w_u);                           // + stage * kStageEnc + (s*2 + plane) * kChunkEnc
             const uint32_t t_rc = tmem_base + kRcCol;
             uint32_t wc = 0;
             if (nseg > 0) {
                 for (int i = 0; i < my_tiles; ++i) {
-                    mbar_wait_p(&tail->a_full, (uint32_t)i & 1, 3);
+                    const int ab = i & 1;
+                    mbar_wait_p(&tail->ahi_full[ab], (uint32_t)(i >> 1) & 1, 3);
                     for (int c = 0; c < 4; ++c, ++wc) {
                         const int stg = wc % kBWStages;
                         const uint32_t ph = (wc / kBWStages) & 1;
@@ -610,27 +645,43 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                         mbar_wait_p(&tail->w_full[stg], ph, 0);
                         mbar_wait_p(&tail->r_empty[b], bph ^ 1, 2);
                         tc_fence_after();
-                        if (lane == 0) {
-                            const uint32_t d = t_rc + (uint32_t)b * 64;
-                            const uint64_t bs = rc_b + (uint64_t)stg * kStageEnc;
+                        const uint32_t d = t_rc + (uint32_t)b * 64;
+                        const uint64_t bs = rc_b + (uint64_t)stg * kStageEnc;
+                        if (lane == 0) {                               // passes on the hi planes (double-buffered: already here)
 #pragma unroll
                             for (int s = 0; s < 2; ++s) {
                                 if (s < nseg) {
-                                    const uint64_t a_hi = rc_a + (uint64_t)(s * 2) * kTileEnc, a_lo = a_hi + kTileEnc;
+                                    const uint64_t a_hi = rc_a + (uint64_t)(ab * 2 + s) * kTileEnc;
                                     const uint64_t b_hi = bs + (uint64_t)(s * 2) * kChunkEnc, b_lo = b_hi + kChunkEnc;
 #pragma unroll
                                     for (int kk = 0; kk < 4; ++kk)
                                         mma_bf16(d, a_hi + kk * kStepK, b_hi + kk * kStepK, idesc_rc, (s > 0 || kk > 0) ? 1u : 0u);
                                     if (PLANES == 2) {
 #pragma unroll
-                                        for (int kk = 0; kk < 4; ++kk) mma_bf16(d, a_lo + kk * kStepK, b_hi + kk * kStepK, idesc_rc, 1u);
-#pragma unroll
                                         for (int kk = 0; kk < 4; ++kk) mma_bf16(d, a_hi + kk * kStepK, b_lo + kk * kStepK, idesc_rc, 1u);
                                     }
                                 }
                             }
-                            mma_commit(&tail->r_full[b]);
                         }
+                        __syncwarp();
+                        if (PLANES == 2) {                             // pass on the lo planes (single buffer: may still be loading)
+                            if (c == 0) {
+                                mbar_wait_p(&tail->alo_full, (uint32_t)i & 1, 3);
+                                tc_fence_after();
+                            }
+                            if (lane == 0) {
+#pragma unroll
+                                for (int s = 0; s < 2; ++s) {
+                                    if (s < nseg) {
+                                        const uint64_t a_lo = rc_a + (uint64_t)(4 + s) * kTileEnc;
+                                        const uint64_t b_hi = bs + (uint64_t)(s * 2) * kChunkEnc;
+#pragma unroll
+                                        for (int kk = 0; kk < 4; ++kk) mma_bf16(d, a_lo + kk * kStepK, b_hi + kk * kStepK, idesc_rc, 1u);
+                                    }
+                                }
+                            }
+                        }
+                        if (lane == 0) mma_commit(&tail->r_full[b]);
                         __syncwarp();
                     }
                 }
@@ -638,30 +689,36 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             TC_PROF_FLUSH(4, lane == 0)
         } else if (role == 1) {
             // ---- W: dWp[:, chunk c] += A'^T . dA_c   (M = kd 128, N = 64, K = 128 rows); one accumulator for the launch ----
-            const uint64_t wg_a = desc16_mn(a_u + wg_a0 * kATileBytes, wg_lbo);   // hi planes; lo: + kTileEnc
-            const uint64_t wg_b = desc16_mn(da_u, kATileBytes);                    // dA hi; lo: + kTileEnc
+            // pass order: the lo-plane pass FIRST, so that the tile's last group releases the single lo buffer a.s.a.p.
+            const uint64_t wg_hi0 = desc16_mn(a_u + wg_a0 * kATileBytes, wg_lbo);              // hi buffer 0; buffer 1: + 2 * kTileEnc
+            const uint64_t wg_lo = desc16_mn(a_u + (4 + wg_a0) * kATileBytes, wg_lbo);         // lo planes
+            const uint64_t wg_b = desc16_mn(da_u, kATileBytes);                                  // dA hi; lo: + kTileEnc
             const uint32_t t_wg = tmem_base + kWgCol;
+            const bool a_sync = nseg > 0 || L0;      // someone waits for the A buffers (producer and / or the aux-tile writers)
             uint32_t dcount = 0;
             for (int i = 0; i < my_tiles; ++i) {
+                const uint64_t wg_hi = wg_hi0 + (uint64_t)((i & 1) * 2) * kTileEnc;
                 for (int c = 0; c < 4; ++c, ++dcount) {
                     mbar_wait_p(&tail->d_full, dcount & 1, 1);
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t d_wg = t_wg + (uint32_t)c * 64;
-                        mma_bf16(d_wg, wg_a, wg_b, idesc_wg, (i > 0) ? 1u : 0u);
-#pragma unroll
-                        for (int ks = 1; ks < 8; ++ks) mma_bf16(d_wg, wg_a + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, 1u);
+                        const uint32_t acc0 = (i > 0) ? 1u : 0u;
                         if (PLANES == 2) {
+                            mma_bf16(d_wg, wg_lo, wg_b, idesc_wg, acc0);
 #pragma unroll
-                            for (int ks = 0; ks < 8; ++ks)
-                                mma_bf16(d_wg, wg_a + kTileEnc + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, 1u);
+                            for (int ks = 1; ks < 8; ++ks) mma_bf16(d_wg, wg_lo + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, 1u);
+                            if (c == 3 && a_sync) mma_commit(&tail->alo_empty);           // lo planes may be refilled
                         }
+                        mma_bf16(d_wg, wg_hi, wg_b, idesc_wg, PLANES == 2 ? 1u : acc0);
+#pragma unroll
+                        for (int ks = 1; ks < 8; ++ks) mma_bf16(d_wg, wg_hi + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, 1u);
                         // dA always has its lo plane (it never leaves the SM, the extra pass is free on an idle tensor pipe):
                         // in the single-plane (bf16 storage) mode only the STORED operands are rounded to bf16
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
-                            mma_bf16(d_wg, wg_a + ks * kStepMN, wg_b + kTileEnc + ks * kStepMN, idesc_wg, 1u);
-                        if (c == 3 && nseg > 0) mma_commit(&tail->a_empty);        // A planes may be refilled
+                            mma_bf16(d_wg, wg_hi + ks * kStepMN, wg_b + kTileEnc + ks * kStepMN, idesc_wg, 1u);
+                        if (c == 3 && a_sync) mma_commit(&tail->ahi_empty[i & 1]);       // this tile's hi buffer may be refilled
                         mma_commit(&tail->d_empty);
                     }
                     __syncwarp();
@@ -781,16 +838,19 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             }
             if (i > 0 && p.nseg > 0) drain(i - 1, tile - gstep);
             if (have_aux && part == 0) {
-                // auxiliary weight-gradient operand: tile 2 (hi) / tile 3 (lo), row = this thread's row, columns 0..C-1 = x*s
-                if (i > 0 && p.nseg > 0) mbar_wait(&tail->a_empty, (uint32_t)(i - 1) & 1, 3);
-                else if (i > 0) mbar_wait(&tail->d_empty, (dcount - 1) & 1, 0);      // no A planes: the last W_3 read the tile
+                // auxiliary weight-gradient operand: the seg-1 slot of this tile's hi buffer and of the lo buffer; row = this
+                // thread's row, columns 0..C-1 = x*s (hi / lo split)
+                if (i >= 2) mbar_wait(&tail->ahi_empty[i & 1], (uint32_t)((i >> 1) - 1) & 1, 3);
                 uint32_t hi[2], lo[2];
                 split_bf16x2(xs[0], xs[1], hi[0], lo[0]);
                 split_bf16x2(xs[2], xs[3], hi[1], lo[1]);
                 const uint32_t row = (uint32_t)(q * 32 + lane);
                 const uint32_t off = row * 128u + ((0u ^ (row & 7u)) << 4);
-                *reinterpret_cast<uint4*>(a_sm + 2 * (size_t)kATileBytes + off) = make_uint4(hi[0], hi[1], 0u, 0u);
-                *reinterpret_cast<uint4*>(a_sm + 3 * (size_t)kATileBytes + off) = make_uint4(lo[0], lo[1], 0u, 0u);
+                *reinterpret_cast<uint4*>(a_sm + (size_t)((i & 1) * 2 + 1) * kATileBytes + off) = make_uint4(hi[0], hi[1], 0u, 0u);
+                if (PLANES == 2) {
+                    if (i >= 1) mbar_wait(&tail->alo_empty, (uint32_t)(i - 1) & 1, 3);
+                    *reinterpret_cast<uint4*>(a_sm + (size_t)5 * kATileBytes + off) = make_uint4(lo[0], lo[1], 0u, 0u);
+                }
             }
             for (int c = 0; c < 4; ++c, ++dcount) {
                 cur = nxt;
