@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
     if (warp == kProdWarp) {
         // ===================== producer: resident weights once, then the A planes of every tile =====================
         TC_PROF_DECL
-        if (lane == 0 && p.nseg > 0) {
+        const bool leader = elect_one_sync();
+        if (leader && p.nseg > 0) {
             mbar_arrive_expect_tx(&tail->w_full, (uint32_t)(p.nseg * PLANES * kWTileBytes));
             for (int s = 0; s < p.nseg; ++s)
                 for (int pl = 0; pl < PLANES; ++pl)
@@ -191,10 +192,11 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                     }
             }
         }
-        TC_PROF_FLUSH(0, lane == 0)
+        TC_PROF_FLUSH(0, leader)
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         TC_PROF_DECL
+        const bool leader = elect_one_sync();
         if (p.nseg > 0) {
             constexpr uint32_t idesc = idesc_bf16(kTileM, kGateCols);
             mbar_wait_p(&tail->w_full, 0, 0);
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                         const uint32_t ph = (it / kFStages) & 1;
                         mbar_wait_p(&tail->full[stg], ph, 1);
                         tc_fence_after();
-                        if (lane == 0) {
+                        if (leader) {
                             const uint64_t a_d = desc16_k(smem_u32(stages + (size_t)stg * kATileBytes));
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                         const uint32_t ph = (it / kFStages) & 1;
                         mbar_wait_p(&tail->full[stg], ph, 1);
                         tc_fence_after();
-                        if (lane == 0) {
+                        if (leader) {
                             const uint64_t a_d = desc16_k(smem_u32(stages + (size_t)stg * kATileBytes));
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
@@ -245,11 +247,11 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                         ++it;
                     }
                 }
-                if (lane == 0) mma_commit(&tail->tmem_full[a]);
+                if (leader) mma_commit(&tail->tmem_full[a]);
                 __syncwarp();
             }
         }
-        TC_PROF_FLUSH(1, lane == 0)
+        TC_PROF_FLUSH(1, leader)
     } else {
         // ===================== epilogue: LSTM cell =====================
         TC_PROF_DECL
@@ -423,22 +425,21 @@ __global__ void lstm16_pack_kernel(const float* __restrict__ w_ih, const float* 
 // the slices once per layer and writes nn.LSTM-native gradients.
 constexpr int kBCompWarps = 16;
 constexpr int kBThreads = (kBCompWarps + 4) * 32;       // + three MMA-issuing warps + producer warp
-constexpr int kBWStages = 2;                            // a weight chunk is held from R_c to D_c: two suffice while the compute
-                                                        // warps, not the tensor pipe, set the pace (a chunk-time >> MMA + reload)
+constexpr int kBWStages = 2;                            // two single-buffered slots: the recompute's and the data gradient's copy
 constexpr int kBWChunkTile = 64 * 128;                  // [64 gate cols][64 k] bf16 = 8 KB
 constexpr int kBWStageBytes = 4 * kBWChunkTile;         // (seg0 hi | seg0 lo | seg1 hi | seg1 lo) = 32 KB
 constexpr int kBSgMax = 1024;
 
 struct B16Tail {
+    uint16_t ones[1024];                       // [16][64] bf16 tile of 1.0: B operand of the bias-gradient MMA (first member:
+                                               // the tail starts 1024-byte aligned, as a swizzled K-major operand must)
     float bias[kGateCols];
     float wih[kMaxC * kGateCols];
-    float s_db[4][kGateCols];                  // bias-gradient partial sums per TMEM lane quadrant: the four warps of a
-                                               // quadrant own disjoint 16-column groups of every chunk (plain adds, no atomics)
     float s_ds[kBSgMax];
     uint64_t ahi_full[2], ahi_empty[2];        // A hi planes: double-buffered by tile parity
     uint64_t alo_full, alo_empty;              // A lo planes: single buffer
     uint64_t w_full[kBWStages], w_empty[kBWStages];
-    uint64_t r_full[2], r_empty[2];
+    uint64_t r_full, r_empty;
     uint64_t d_full, d_empty;
     uint64_t g_full, g_empty;
     uint64_t done;
@@ -496,7 +497,9 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     constexpr int kMmaWarp = kBCompWarps;
     constexpr int kProdWarp = kBCompWarps + 3;
     constexpr int kCompThreads = kBCompWarps * 32;
-    constexpr uint32_t kWgCol = 0, kDgCol = 256, kRcCol = 384;     // TMEM columns: weight grad | data grad | recompute x2
+    // TMEM columns: weight grad (256) | data grad (128) | recompute (64, single buffer: the compute warps hold it only for
+    // the TMEM -> register copy at the start of a chunk) | bias grad (4 chunks x 16)
+    constexpr uint32_t kWgCol = 0, kDgCol = 256, kRcCol = 384, kDbCol = 448;
 
     if (tid == 0) {
         for (int b = 0; b < 2; ++b) {
@@ -509,10 +512,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             mbar_init(&tail->w_full[s], 1);
             mbar_init(&tail->w_empty[s], 1);
         }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&tail->r_full[b], 1);
-            mbar_init(&tail->r_empty[b], kBCompWarps);         // one arrival per compute warp
-        }
+        mbar_init(&tail->r_full, 1);
+        mbar_init(&tail->r_empty, kBCompWarps);                // one arrival per compute warp
         mbar_init(&tail->d_full, kBCompWarps);
         mbar_init(&tail->d_empty, 2);                          // weight-gradient warp + data-gradient warp
         mbar_init(&tail->g_full, 1);
@@ -522,11 +523,12 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     }
     if (warp == kMmaWarp) tmem_alloc(&tail->tmem_base, 512);
     for (int i = tid; i < kGateCols; i += kBThreads) tail->bias[i] = p.bias[i] * gate_scale(i);
-    for (int i = tid; i < 4 * kGateCols; i += kBThreads) (&tail->s_db[0][0])[i] = 0.f;
+    for (int i = tid; i < 1024; i += kBThreads) tail->ones[i] = 0x3f80u;           // bf16 1.0 (layout-invariant)
     if (L0) {
         for (int i = tid; i < p.c_in * kGateCols; i += kBThreads) tail->wih[i] = p.wih[i] * gate_scale(i);
         for (int i = tid; i < kBSgMax; i += kBThreads) tail->s_ds[i] = 0.f;
     }
+    fence_proxy_async_smem();                   // the ones tile is read by the tensor pipe (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -542,7 +544,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     if (warp == kProdWarp) {
         // ===================== producer =====================
         TC_PROF_DECL
-        if (lane == 0 && p.nseg > 0 && my_tiles > 0) {
+        const bool leader = elect_one_sync();
+        if (leader && p.nseg > 0 && my_tiles > 0) {
             const int first = (int)blockIdx.x, gstep = (int)gridDim.x;
             auto load_hi = [&](int i) {                 // hi planes of tile i -> hi buffer i & 1
                 const int b = i & 1;
@@ -559,10 +562,9 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     tma_load_3d(a_sm + (size_t)(4 + s) * kATileBytes, &p.amap[s], 0, (first + i * gstep) * kTileM, p.aslice[s] + 1,
                                 &tail->alo_full);
             };
-            auto load_w = [&](uint32_t wc) {            // weight chunk wc & 3 -> ring stage wc % kBWStages
-                const int stg = wc % kBWStages, c = wc & 3;
-                const uint32_t ph = (wc / kBWStages) & 1;
-                mbar_wait_p(&tail->w_empty[stg], ph ^ 1, 0);
+            auto load_w = [&](int stg, uint32_t wc) {   // weight chunk wc & 3 -> buffer stg (0: the recompute's copy, 1: the
+                const int c = wc & 3;                   // data gradient's copy); use wc of a buffer waits for release wc - 1
+                mbar_wait_p(&tail->w_empty[stg], (wc & 1) ^ 1, 0);
                 mbar_arrive_expect_tx(&tail->w_full[stg], (uint32_t)(p.nseg * PLANES * kBWChunkTile));
                 for (int s = 0; s < p.nseg; ++s)
                     for (int pl = 0; pl < PLANES; ++pl)
@@ -584,30 +586,39 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     prefetch_l2(p.dc + o, kB);
                 }
             };
-            // Flat schedule.  Every wait below is on an event that lies in the PAST of what the consumers need next, so the
-            // single producer thread never delays a consumer: weight chunk (i+1, 0) is requested as soon as D_2(i) has released
-            // its stage, before the wait for the lo buffer (released by W_3(i)), so the first recompute of tile i+1 is in
-            // flight while the compute warps are still on the last chunk of tile i.
+            // Every weight chunk is loaded TWICE (L2 hits), into two single-buffered slots: one copy for the recompute R_c, one
+            // for the data gradient D_c.  With one shared ring a stage was held from R_c until D_c (a whole chunk-time later), so
+            // R_{c+2} had to wait for D_c + a reload + its own MMAs inside one chunk-time: the recompute warp spent 40 % of its
+            // life waiting for weights and the compute warps 11 % waiting for the recompute.  Now R_{c+1} only needs the compute
+            // warps to have copied G_c out of TMEM.
+            // Flat schedule: every wait below is on an event that lies in the PAST of what the consumers need next, in time
+            // order: R(g+2) is released at the start of chunk-time g+1, D(g+1)'s buffer at the end of chunk-time g.
             load_hi(0);
             if (PLANES == 2) load_lo(0);
-            load_w(0);
-            load_w(1);
+            load_w(0, 0);
+            load_w(1, 0);
+            load_w(0, 1);
             for (int i = 0; i < my_tiles; ++i) {
                 const bool more = i + 1 < my_tiles;
+                const uint32_t g0 = 4u * (uint32_t)i;
                 if (more) {
                     load_hi(i + 1);
                     prefetch_next(i + 1);
                 }
-                load_w((uint32_t)(4 * i + 2));
-                load_w((uint32_t)(4 * i + 3));
+                load_w(0, g0 + 2);
+                load_w(1, g0 + 1);
+                load_w(0, g0 + 3);
+                load_w(1, g0 + 2);
+                if (more) load_w(0, g0 + 4);
+                load_w(1, g0 + 3);
                 if (more) {
-                    load_w((uint32_t)(4 * i + 4));
                     if (PLANES == 2) load_lo(i + 1);
-                    load_w((uint32_t)(4 * i + 5));
+                    load_w(0, g0 + 5);
+                    load_w(1, g0 + 4);
                 }
             }
         }
-        TC_PROF_FLUSH(5, lane == 0)
+        TC_PROF_FLUSH(5, leader)
     } else if (warp >= kMmaWarp && warp < kProdWarp) {
         // ===================== three MMA issuers: recompute (R) | weight gradient (W) | data gradient (D) =====================
         // A tile needs ~240 tcgen05.mma instructions; issued by ONE thread they cost ~90 cycles apiece (ptxas moves every
@@ -618,6 +629,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         // Everything that does not change is hoisted into 64-bit descriptor constants; a k-step is one add on the
         // descriptor's address field (encoded address = bytes >> 4; all operands live below 256 KB: no carry).
         TC_PROF_DECL
+        const bool leader = elect_one_sync();
         constexpr uint32_t idesc_rc = idesc_bf16(kTileM, 64);              // recompute: A K-major, B K-major, N = 64
         constexpr uint32_t idesc_wg = idesc_bf16(kTileM, 64, 1, 1);        // weight gradient: both MN-major, M = kd (128), N = 64
         const uint32_t idesc_dg = idesc_bf16(kTileM, 64 * (p.nseg > 0 ? p.nseg : 1), 0, 1);   // data gradient: B MN-major, N = 64 * nseg
@@ -628,7 +640,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         const int nseg = p.nseg;
         const int role = warp - kMmaWarp;                                  // 0: R, 1: W, 2: D
         if (role == 0) {
-            // ---- R: G_c[128 x 64] = [h_below | h_prev] . Wp[:, chunk c]  into one of two TMEM buffers ----
+            // ---- R: G_c[128 x 64] = [h_below | h_prev] . Wp[:, chunk c] ----
             const uint64_t rc_a = desc16_k(a_u);                           // hi: + (buffer*2 + s) * kTileEnc; lo: + (4 + s) * kTileEnc
             const uint64_t rc_b = desc16_k(w_u);                           // + stage * kStageEnc + (s*2 + plane) * kChunkEnc
             const uint32_t t_rc = tmem_base + kRcCol;
@@ -638,16 +650,12 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     const int ab = i & 1;
                     mbar_wait_p(&tail->ahi_full[ab], (uint32_t)(i >> 1) & 1, 3);
                     for (int c = 0; c < 4; ++c, ++wc) {
-                        const int stg = wc % kBWStages;
-                        const uint32_t ph = (wc / kBWStages) & 1;
-                        const int b = wc & 1;
-                        const uint32_t bph = (wc >> 1) & 1;
-                        mbar_wait_p(&tail->w_full[stg], ph, 0);
-                        mbar_wait_p(&tail->r_empty[b], bph ^ 1, 2);
+                        mbar_wait_p(&tail->w_full[0], wc & 1, 0);
+                        mbar_wait_p(&tail->r_empty, (wc & 1) ^ 1, 2);
                         tc_fence_after();
-                        const uint32_t d = t_rc + (uint32_t)b * 64;
-                        const uint64_t bs = rc_b + (uint64_t)stg * kStageEnc;
-                        if (lane == 0) {                               // passes on the hi planes (double-buffered: already here)
+                        const uint32_t d = t_rc;
+                        const uint64_t bs = rc_b;                   // buffer 0: the recompute's copy of the chunk
+                        if (leader) {                               // passes on the hi planes (double-buffered: already here)
 #pragma unroll
                             for (int s = 0; s < 2; ++s) {
                                 if (s < nseg) {
@@ -669,7 +677,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                                 mbar_wait_p(&tail->alo_full, (uint32_t)i & 1, 3);
                                 tc_fence_after();
                             }
-                            if (lane == 0) {
+                            if (leader) {
 #pragma unroll
                                 for (int s = 0; s < 2; ++s) {
                                     if (s < nseg) {
@@ -681,12 +689,15 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                                 }
                             }
                         }
-                        if (lane == 0) mma_commit(&tail->r_full[b]);
+                        if (leader) {
+                            mma_commit(&tail->w_empty[0]);
+                            mma_commit(&tail->r_full);
+                        }
                         __syncwarp();
                     }
                 }
             }
-            TC_PROF_FLUSH(4, lane == 0)
+            TC_PROF_FLUSH(4, leader)
         } else if (role == 1) {
             // ---- W: dWp[:, chunk c] += A'^T . dA_c   (M = kd 128, N = 64, K = 128 rows); one accumulator for the launch ----
             // pass order: the lo-plane pass FIRST, so that the tile's last group releases the single lo buffer a.s.a.p.
@@ -694,6 +705,13 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             const uint64_t wg_lo = desc16_mn(a_u + (4 + wg_a0) * kATileBytes, wg_lbo);         // lo planes
             const uint64_t wg_b = desc16_mn(da_u, kATileBytes);                                  // dA hi; lo: + kTileEnc
             const uint32_t t_wg = tmem_base + kWgCol;
+            // bias gradient on the tensor pipe: D[128 x 16] += dA_c^T (MN-major A, M = 64 columns of the hi plane | 64 of the
+            // lo plane: the two planes are the two 64-element atoms, LBO = one tile) . ones[K = 16 rows][16].  Lane m < 64 of
+            // the accumulator holds sum_rows hi(dA)[:, m], lane 64 + m the lo plane's sum; all 16 columns are equal.  (The
+            // shuffle butterfly this replaces was 21 % of the compute warps' stall samples.)
+            constexpr uint32_t idesc_db = idesc_bf16(kTileM, 16, 1, 0);
+            const uint64_t db_b = desc16_k(smem_u32(tail->ones));
+            const uint32_t t_db = tmem_base + kDbCol;
             const bool a_sync = nseg > 0 || L0;      // someone waits for the A buffers (producer and / or the aux-tile writers)
             uint32_t dcount = 0;
             for (int i = 0; i < my_tiles; ++i) {
@@ -701,7 +719,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 for (int c = 0; c < 4; ++c, ++dcount) {
                     mbar_wait_p(&tail->d_full, dcount & 1, 1);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (leader) {
                         const uint32_t d_wg = t_wg + (uint32_t)c * 64;
                         const uint32_t acc0 = (i > 0) ? 1u : 0u;
                         if (PLANES == 2) {
@@ -719,14 +737,17 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                         for (int ks = 0; ks < 8; ++ks)
                             mma_bf16(d_wg, wg_hi + ks * kStepMN, wg_b + kTileEnc + ks * kStepMN, idesc_wg, 1u);
                         if (c == 3 && a_sync) mma_commit(&tail->ahi_empty[i & 1]);       // this tile's hi buffer may be refilled
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            mma_bf16(t_db + (uint32_t)c * 16, wg_b + ks * kStepMN, db_b, idesc_db, (i > 0 || ks > 0) ? 1u : 0u);
                         mma_commit(&tail->d_empty);
                     }
                     __syncwarp();
                 }
             }
-            if (lane == 0) mma_commit(&tail->done);
+            if (leader) mma_commit(&tail->done);
             __syncwarp();
-            TC_PROF_FLUSH(6, lane == 0)
+            TC_PROF_FLUSH(6, leader)
         } else {
             // ---- D: [dx_below | dh_prev] += dA_c . Wp[:, chunk c]^T   (N = 64 * nseg, K = 64) ----
             const uint64_t dg_a = desc16_k(da_u);                              // dA hi; lo: + kTileEnc
@@ -735,13 +756,13 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             uint32_t dcount = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 for (int c = 0; c < 4; ++c, ++dcount) {
+                    if (nseg > 0) mbar_wait_p(&tail->w_full[1], dcount & 1, 0);
                     mbar_wait_p(&tail->d_full, dcount & 1, 1);
                     if (c == 0 && nseg > 0 && i > 0) mbar_wait_p(&tail->g_empty, (uint32_t)(i - 1) & 1, 2);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (leader) {
                         if (nseg > 0) {
-                            const int stg = dcount % kBWStages;
-                            const uint64_t bs = dg_b + (uint64_t)stg * kStageEnc;
+                            const uint64_t bs = dg_b + kStageEnc;          // buffer 1: the data gradient's copy of the chunk
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
                                 mma_bf16(t_dg, dg_a + kk * kStepK, bs + kk * kStepMN, idesc_dg, (c > 0 || kk > 0) ? 1u : 0u);
@@ -753,7 +774,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                                 for (int kk = 0; kk < 4; ++kk)
                                     mma_bf16(t_dg, dg_a + kk * kStepK, bs + kChunkEnc + kk * kStepMN, idesc_dg, 1u);
                             }
-                            mma_commit(&tail->w_empty[stg]);
+                            mma_commit(&tail->w_empty[1]);
                         }
                         mma_commit(&tail->d_empty);
                         if (c == 3 && nseg > 0) mma_commit(&tail->g_full);
@@ -761,7 +782,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     __syncwarp();
                 }
             }
-            TC_PROF_FLUSH(7, lane == 0)
+            TC_PROF_FLUSH(7, leader)
         }
     } else {
         // ===================== compute warps =====================
@@ -809,9 +830,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 if (r < rows32 && base != nullptr && (is_dx || p.store_dh)) {
                     const uint32_t o = (uint32_t)tile_prev * 8192u + row_in_tile * 8u + (uint32_t)(unit0 >> 3) * 1024u;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)          // units unit0 + 4j: (j >> 1) 8-unit groups on, half (j & 1)
-                        *reinterpret_cast<uint4*>(base + (o + (uint32_t)(j >> 1) * 1024u + (uint32_t)(j & 1) * 4u)) =
-                            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int m = 0; m < 4; ++m)          // units unit0 + 8m .. +7: one 32-byte run per row -> a warp writes 1 KB
+                        st_global_v8(base + (o + (uint32_t)m * 1024u), &v[8 * m]);   // contiguous (256-bit stores: full sectors)
                 }
             }
             tc_fence_before();
@@ -822,7 +842,6 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         const int gstep = (int)gridDim.x;
         int tile = (int)blockIdx.x;
         load_raw(tile, 0, nxt);
-        float* my_db = tail->s_db[q];              // this quadrant's bias-gradient accumulators (this warp: its own columns)
         for (int i = 0; i < my_tiles; ++i, tile += gstep) {
             const uint32_t r = (uint32_t)tile * kTileM + row_in_tile;
             const bool valid = r < rows32;
@@ -836,6 +855,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     dxs[c] = 0.f;
                 }
             }
+            // (the drain sits in the tile-boundary bubble: the first recompute of this tile cannot finish before the lo planes
+            // have been reloaded; moved behind chunk 0 it cost 2.3 k cycles of real time per tile, measured)
             if (i > 0 && p.nseg > 0) drain(i - 1, tile - gstep);
             if (have_aux && part == 0) {
                 // auxiliary weight-gradient operand: the seg-1 slot of this tile's hi buffer and of the lo buffer; row = this
@@ -856,14 +877,13 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 cur = nxt;
                 uint32_t v[16];
                 if (p.nseg > 0) {
-                    const int b = rcount & 1;
-                    mbar_wait(&tail->r_full[b], (rcount >> 1) & 1, 1);
+                    mbar_wait(&tail->r_full, rcount & 1, c == 0 ? 3 : 1);      // (profile builds: class 3 = first chunk of a tile)
                     tc_fence_after();
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kRcCol + (uint32_t)b * 64 + (uint32_t)part * 16, v);
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kRcCol + (uint32_t)part * 16, v);
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tail->r_empty[b]);
+                    if (lane == 0) mbar_arrive(&tail->r_empty);
                     ++rcount;
                 } else {
 #pragma unroll
@@ -937,40 +957,6 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 if (valid)
                     *reinterpret_cast<float4*>(p.dc + ((uint32_t)tile * 8192u + (uint32_t)c * 2048u + thr_off)) =
                         make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
-                // bias gradient: column sums over the warp's 32 rows by a halving butterfly (16 shuffles), then one
-                // shared-memory atomic per column from the even lanes
-                {
-                    float s8[8], s4[4], s2[2], s1;
-                    const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0, u2 = (lane & 2) != 0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float send = u16 ? da[j] : da[j + 8];
-                        const float keep = u16 ? da[j + 8] : da[j];
-                        s8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float send = u8 ? s8[j] : s8[j + 4];
-                        const float keep = u8 ? s8[j + 4] : s8[j];
-                        s4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const float send = u4 ? s4[j] : s4[j + 2];
-                        const float keep = u4 ? s4[j + 2] : s4[j];
-                        s2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    {
-                        const float send = u2 ? s2[0] : s2[1];
-                        const float keep = u2 ? s2[1] : s2[0];
-                        s1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                    }
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-                    if ((lane & 1) == 0) {         // (shared-memory float atomics compile to CAS spin loops: private rows instead)
-                        const int j = (u16 ? 8 : 0) + (u8 ? 4 : 0) + (u4 ? 2 : 0) + (u2 ? 1 : 0);
-                        my_db[4 * unit0 + j] += s1;
-                    }
-                }
             }
             if (L0 && valid) {
                 // gate adjoint: d s[b, t] += sum_c dxmod[r, c] * xo[r, t, c]   (STMGCN.py:44)
@@ -990,6 +976,15 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             tc_fence_after();
             float* slice = p.dw_slice + (size_t)blockIdx.x * (kTileM * kGateCols);
             const int m = q * 32 + lane;
+            if (part == 0) {                       // bias gradient: lanes [0,64) hold the hi-plane sums, [64,128) the lo-plane sums
+                uint32_t v[16];
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kDbCol + (uint32_t)c * 16, v);
+                    tmem_ld_wait();
+                    atomicAdd(&p.dbp[64 * c + (m & 63)], __uint_as_float(v[0]));
+                }
+            }
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
                 uint32_t v[16];
@@ -1002,11 +997,11 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                                              __uint_as_float(v[4 * e + 3]));
                     const bool live = (q < 2) ? (p.flush_lo != 0) : (p.flush_hi != 0);      // rows m < 64 / m >= 64
                     if (live) {
-                        if (!p.dw_first) {
-                            const float4 old = *dst;
-                            acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
-                        }
-                        *dst = acc;
+                        // later launches of the layer add with a fire-and-forget vector reduction (the slice is private to
+                        // this CTA: no contention); a read-modify-write here waited a DRAM round trip at the very end of
+                        // every launch, where nothing overlaps it
+                        if (!p.dw_first) red_add_f32x4(dst, acc);
+                        else *dst = acc;
                     } else if (p.dw_first) {
                         *dst = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
@@ -1018,12 +1013,6 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
-    for (int i = tid; i < kGateCols; i += kBThreads) {
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) v += tail->s_db[w][i];
-        atomicAdd(&p.dbp[i], v);
-    }
     if (L0 && p.b_inner <= kBSgMax)
         for (int i = tid; i < (int)p.b_inner; i += kBThreads) atomicAdd(&p.d_s[(int64_t)i * p.t_len + p.t], tail->s_ds[i]);
 }

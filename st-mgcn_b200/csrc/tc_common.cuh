@@ -108,6 +108,26 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 
 // L2 prefetch of a contiguous global range (no registers, no shared memory; SASS UBLKPF)
+// One elected lane of a fully converged warp.  Guarding the single-thread tcgen05 / TMA / mbarrier instructions with this
+// instead of `lane == 0` matters: ptxas cannot prove `lane == 0` selects one thread, and wraps EVERY uniform-datapath
+// instruction (UTCHMMA, UTCBAR, UBLKCP, UTMALDG) in an ELECT / BRA.U.ANY serialisation loop -- ~10 extra instructions and
+// a branch per MMA, measured as ~90 cycles per issued tcgen05.mma.  After elect.sync the instructions issue back to back.
+// The elected lane is the same on every call of a converged warp, so MMAs and their tcgen05.commit come from one thread.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// 256-bit global store / load (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256): 8 consecutive 32-bit words, 32-byte aligned
+__device__ __forceinline__ void st_global_v8(float* dst, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+// fire-and-forget 16-byte reduction into global memory (REDG.E.ADD.F32x4: the add happens in L2, nothing returns)
+__device__ __forceinline__ void red_add_f32x4(float4* dst, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* gmem, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }

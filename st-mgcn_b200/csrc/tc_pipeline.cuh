@@ -40,6 +40,8 @@ __device__ __forceinline__ void mma_issuer(Barriers* bar, uint8_t* smem, int sta
                                            int n_tiles, uint32_t tmem_base, int lane) {
     constexpr uint32_t idesc = idesc_tf32(kTileM, N);
     TC_PROF_DECL
+    (void)lane;
+    const bool leader = elect_one_sync();      // (not `leader`: see elect_one_sync in tc_common.cuh)
     uint32_t it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         const int a = tcount & 1;
@@ -52,7 +54,7 @@ __device__ __forceinline__ void mma_issuer(Barriers* bar, uint8_t* smem, int sta
             const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(&bar->full[s], ph, 1);
             tc_fence_after();
-            if (lane == 0) {
+            if (leader) {
                 const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t a_hi = smem_desc_k_sw128(st);
                 const uint64_t a_lo = smem_desc_k_sw128(st + kABytes);
@@ -72,10 +74,10 @@ __device__ __forceinline__ void mma_issuer(Barriers* bar, uint8_t* smem, int sta
             }
             __syncwarp();
         }
-        if (lane == 0) mma_commit(&bar->tmem_full[a]);
+        if (leader) mma_commit(&bar->tmem_full[a]);
         __syncwarp();
     }
-    TC_PROF_FLUSH(PROF_KERNEL * 3 + 1, lane == 0)
+    TC_PROF_FLUSH(PROF_KERNEL * 3 + 1, leader)
 }
 
 __device__ __forceinline__ void split_store(uint8_t* st, uint32_t off, const float4& v) {

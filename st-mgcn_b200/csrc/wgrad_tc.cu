@@ -166,13 +166,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
         constexpr uint32_t idesc = idesc_tf32(128, N, 1);          // both operands MN-major
         constexpr uint32_t kLbo = (kWgRows / 4) * 512, kSbo = 512;
         TC_PROF_DECL
+        const bool leader = elect_one_sync();      // (not `leader`: see elect_one_sync in tc_common.cuh)
         uint32_t it = 0;
         for (int64_t chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x, ++it) {
             const int s = it % kWgStages;
             const uint32_t ph = (it / kWgStages) & 1;
             mbar_wait(&tail->full[s], ph, 1);
             tc_fence_after();
-            if (lane == 0) {
+            if (leader) {
                 const uint32_t st = smem_u32(smem + (size_t)s * kWgStageBytes);
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
@@ -189,9 +190,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) lstm_wgrad_tc_kernel(const __gr
             }
             __syncwarp();
         }
-        if (lane == 0 && has_work) mma_commit(&tail->done);
+        if (leader && has_work) mma_commit(&tail->done);
         __syncwarp();
-        TC_PROF_FLUSH(10, lane == 0)
+        TC_PROF_FLUSH(10, leader)
     }
     tc_fence_before();
     __syncthreads();
