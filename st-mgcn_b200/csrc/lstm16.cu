@@ -6,7 +6,10 @@
 //        arithmetic; P = 1: hi only, the bf16 mode).  A 128-row x 64-column piece of a plane IS a K-major, 128-byte
 //        swizzled tcgen05 operand tile once a TMA tensor load has put it into shared memory -- no splitter warps, no
 //        per-thread loads, no proxy fences on the operand path.
-//   cs : (L, T, rows_pad, 64) fp32, tile-blocked ([tile][unit/8][128 rows][8 units], see ws_off).
+//   cs : (L, T, rows_pad, 64) fp32, tile-blocked ([tile][unit/4][128 rows][4 units], see ws_off): the 32 lanes of a warp
+//        (32 consecutive rows, the same 4 units) touch ONE contiguous 512-byte run per access.  (With 8-unit groups every
+//        access was 16 bytes at a 32-byte stride: 32 half-used sectors and ~22 L1 data-pipe wavefronts per request; ncu
+//        showed the L1 data pipe -- tensor-core operand reads + LSU -- at 77 % (forward) / 90 % (backward) of its peak.)
 // 4 + 4 bytes per (row, unit, layer-step) instead of 4 + 4 + 16 with the gate tape of the first generation
 // (lstm_tc.cu): 4.8 GB instead of 14.5 GB per graph branch at BASELINE configs[2], and configs[4] fits.
 //
@@ -41,7 +44,7 @@ constexpr int kATileBytes = kTile16Bytes;             // [128 rows][64 k] bf16 =
 
 // element (row r, unit u) of a tile-blocked (rows_pad x 64) fp32 workspace
 __device__ __forceinline__ int64_t ws_off(int64_t r, int unit) {
-    return (((r >> 7) * 8 + (unit >> 3)) * kTileM + (r & 127)) * 8 + (unit & 7);
+    return (((r >> 7) * 16 + (unit >> 2)) * kTileM + (r & 127)) * 4 + (unit & 3);
 }
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
@@ -268,13 +271,13 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
         // that spilled were re-read from local memory in the tile loop at full L1-miss latency (ncu: 18 % of the samples)
         const uint32_t row_in_tile = (uint32_t)(q * 32 + lane);
         const uint32_t rows32 = (uint32_t)p.rows;
-        // tile-blocked (rows_pad x 64): element (tile, row, unit) at tile*8192 + (unit/8)*1024 + row*8 + unit%8
-        const uint32_t thr_c = row_in_tile * 8u + (uint32_t)part * 2048u;
+        // tile-blocked (rows_pad x 64): element (tile, row, unit) at tile*8192 + (unit/4)*512 + row*4 + unit%4
+        const uint32_t thr_c = row_in_tile * 4u + (uint32_t)part * 2048u;
         auto load_c4 = [&](int tile_n, int j) {
             const uint32_t rn = (uint32_t)tile_n * kTileM + row_in_tile;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.c_prev != nullptr && tile_n < p.n_tiles && rn < rows32)
-                v = *reinterpret_cast<const float4*>(p.c_prev + ((uint32_t)tile_n * 8192u + thr_c + (uint32_t)(j >> 1) * 1024u + (uint32_t)(j & 1) * 4u));
+                v = *reinterpret_cast<const float4*>(p.c_prev + ((uint32_t)tile_n * 8192u + thr_c + (uint32_t)j * 512u));
             cpv[4 * j] = v.x; cpv[4 * j + 1] = v.y; cpv[4 * j + 2] = v.z; cpv[4 * j + 3] = v.w;
         };
         auto load_xs = [&](int tile_n, float (&dst)[kMaxC]) {
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                     hi[2 * pc + 1] = pack_bf16x2(hn[2], hn[3]);
                 }
                 if (valid) {
-                    *reinterpret_cast<float4*>(p.c_out + ((uint32_t)tile * 8192u + thr_c + (uint32_t)(pc >> 1) * 1024u + (uint32_t)(pc & 1) * 4u)) =
+                    *reinterpret_cast<float4*>(p.c_out + ((uint32_t)tile * 8192u + thr_c + (uint32_t)pc * 512u)) =
                         make_float4(cn[0], cn[1], cn[2], cn[3]);
                     if (p.h_f32 != nullptr)
                         *reinterpret_cast<float4*>(p.h_f32 + (r * (uint32_t)kHid + (uint32_t)unit0)) = make_float4(hn[0], hn[1], hn[2], hn[3]);
@@ -356,14 +359,9 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                 if (lane == 0) mbar_arrive(&tail->tmem_empty[a]);
             }
             if (valid) {
-                uint4* dh = reinterpret_cast<uint4*>(p.h_hi + (r * (uint32_t)kHid + (uint32_t)part * 16u));
-                dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                if (PLANES == 2) {
-                    uint4* dl = reinterpret_cast<uint4*>(p.h_lo + (r * (uint32_t)kHid + (uint32_t)part * 16u));
-                    dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-                }
+                // 16 bf16 = 32 bytes per row and plane: one 256-bit store (a full sector) instead of two 128-bit ones
+                st_global_v8(p.h_hi + (r * (uint32_t)kHid + (uint32_t)part * 16u), hi);
+                if (PLANES == 2) st_global_v8(p.h_lo + (r * (uint32_t)kHid + (uint32_t)part * 16u), lo);
             }
             if (l0) {
 #pragma unroll
@@ -795,10 +793,10 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         uint32_t dcount = 0, rcount = 0;
         // raw inputs of one chunk: c_prev, dh_in, dh_rec, dc of this thread's 4 units
         struct Raw { float4 cp, dhi, dhr, dcv; };
-        // tile-blocked workspaces: element (tile, row, unit) at tile*8192 + (unit/8)*1024 + row*8 + unit%8
+        // tile-blocked workspaces: element (tile, row, unit) at tile*8192 + (unit/4)*512 + row*4 + unit%4
         const uint32_t row_in_tile = (uint32_t)(q * 32 + lane);
         const uint32_t rows32 = (uint32_t)p.rows;       // (rows <= 2^25 is checked on the host: 32-bit element offsets)
-        const uint32_t thr_off = row_in_tile * 8u + (uint32_t)(part >> 1) * 1024u + (uint32_t)(part & 1) * 4u;
+        const uint32_t thr_off = row_in_tile * 4u + (uint32_t)part * 512u;
         auto load_raw = [&](int tile, int c, Raw& rw) {
             const uint32_t r = (uint32_t)tile * kTileM + row_in_tile;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -828,10 +826,10 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 float* base = is_dx ? p.dx_out : p.dh_rec;
                 const int unit0 = col & 63;
                 if (r < rows32 && base != nullptr && (is_dx || p.store_dh)) {
-                    const uint32_t o = (uint32_t)tile_prev * 8192u + row_in_tile * 8u + (uint32_t)(unit0 >> 3) * 1024u;
+                    const uint32_t o = (uint32_t)tile_prev * 8192u + row_in_tile * 4u + (uint32_t)(unit0 >> 2) * 512u;
 #pragma unroll
-                    for (int m = 0; m < 4; ++m)          // units unit0 + 8m .. +7: one 32-byte run per row -> a warp writes 1 KB
-                        st_global_v8(base + (o + (uint32_t)m * 1024u), &v[8 * m]);   // contiguous (256-bit stores: full sectors)
+                    for (int k = 0; k < 8; ++k)          // units unit0 + 4k .. +3: the warp writes one contiguous 512-byte run
+                        *reinterpret_cast<uint4*>(base + (o + (uint32_t)k * 512u)) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                 }
             }
             tc_fence_before();

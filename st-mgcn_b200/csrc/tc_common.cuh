@@ -119,7 +119,7 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 // 256-bit global store / load (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256): 8 consecutive 32-bit words, 32-byte aligned
-__device__ __forceinline__ void st_global_v8(float* dst, const uint32_t* v) {
+__device__ __forceinline__ void st_global_v8(void* dst, const uint32_t* v) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                  "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");

@@ -293,20 +293,20 @@ class ContextGate(torch.autograd.Function):
 
 
 def to_blocked(x: torch.Tensor) -> torch.Tensor:
-    """(..., R, 64) row-major -> tile-blocked (..., ceil(R/128)*128, 64) flat layout [tile][unit/8][128][8]."""
+    """(..., R, 64) row-major -> tile-blocked (..., ceil(R/128)*128, 64) flat layout [tile][unit/4][128][4]."""
     *lead, r, h = x.shape
     rp = ((r + 127) // 128) * 128
     if rp != r:
         pad = x.new_zeros(*lead, rp, h)
         pad[..., :r, :] = x
         x = pad
-    return x.reshape(*lead, rp // 128, 128, 8, 8).transpose(-3, -2).contiguous().reshape(*lead, rp, h)
+    return x.reshape(*lead, rp // 128, 128, 16, 4).transpose(-3, -2).contiguous().reshape(*lead, rp, h)
 
 
 def from_blocked(x: torch.Tensor, rows: int) -> torch.Tensor:
     """Inverse of :func:`to_blocked`."""
     *lead, rp, h = x.shape
-    return x.reshape(*lead, rp // 128, 8, 128, 8).transpose(-3, -2).reshape(*lead, rp, h)[..., :rows, :].contiguous()
+    return x.reshape(*lead, rp // 128, 16, 128, 4).transpose(-3, -2).reshape(*lead, rp, h)[..., :rows, :].contiguous()
 
 
 def _pack_lstm(weights: Sequence[torch.Tensor], n_layers: int, hid: int):

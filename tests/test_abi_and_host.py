@@ -143,7 +143,7 @@ def test_lstm_weight_packing_roundtrip():
 @pytest.mark.parametrize("rows", [128, 300, 1])
 def test_tile_blocked_layout_roundtrip_and_formula(rows):
     """to_blocked / from_blocked are inverse, pad to whole 128-row tiles, and place element (r, u) where the kernels'
-    ws_off() expects it: (((r/128)*8 + u/8)*128 + r%128)*8 + u%8  (include/stmgcn_b200.h, stmgcn_lstm_step_bwd)."""
+    ws_off() expects it: (((r/128)*16 + u/4)*128 + r%128)*4 + u%4  (include/stmgcn_b200.h, stmgcn_lstm16_step_fwd)."""
     from stmgcn_b200 import ops
     gen = torch.Generator().manual_seed(rows)
     x = torch.randn(2, rows, 64, generator=gen)
@@ -153,7 +153,7 @@ def test_tile_blocked_layout_roundtrip_and_formula(rows):
     assert torch.equal(ops.from_blocked(blk, rows), x)
     flat = blk.reshape(2, -1)
     for r, u in [(0, 0), (rows - 1, 63), (rows // 2, 9), (min(rows - 1, 127), 8)]:
-        off = (((r // 128) * 8 + u // 8) * 128 + r % 128) * 8 + u % 8
+        off = (((r // 128) * 16 + u // 4) * 128 + r % 128) * 4 + u % 4
         assert float(flat[1, off]) == float(x[1, r, u])
     if rp != rows:                                           # padding rows are zero
         back = ops.from_blocked(blk, rp)
