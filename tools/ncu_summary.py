@@ -18,6 +18,12 @@ WANT = [
     "smsp__warps_active.avg.per_cycle_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "sm__cycles_elapsed.avg", "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size",
     "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    # the L1 / shared-memory data pipe: tensor-core operand reads and LSU traffic share it
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
 ]
 
 
