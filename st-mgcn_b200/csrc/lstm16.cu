@@ -132,8 +132,12 @@ struct Fwd16Params {
     int n_tiles;
 };
 
-template <int PLANES, bool L0>
+// CIN: 0 = not layer 0; 1 = layer 0 with one input channel (the reference's input_dim, compile-time: no predicated-off
+// W_ih FMAs / loads in the cell loop); kMaxC = layer 0 with a runtime channel count <= kMaxC
+template <int PLANES, int CIN>
 __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_constant__ Fwd16Params p) {
+    constexpr bool L0 = CIN > 0;
+    constexpr int kC = (CIN == 1) ? 1 : kMaxC;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would make every access through
     // `smem` a generic LD/ST/ATOM instead of LDS/STS/ATOMS: ncu showed the bias loads as long-scoreboard stalls)
@@ -281,12 +285,13 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
             cpv[4 * j] = v.x; cpv[4 * j + 1] = v.y; cpv[4 * j + 2] = v.z; cpv[4 * j + 3] = v.w;
         };
         auto load_xs = [&](int tile_n, float (&dst)[kMaxC]) {
-            const int64_t rn = (int64_t)tile_n * kTileM + q * 32 + lane;
-            const bool ok = tile_n < p.n_tiles && rn < p.rows;
+            const uint32_t rn = (uint32_t)tile_n * kTileM + row_in_tile;
+            const bool ok = tile_n < p.n_tiles && rn < rows32;
             float sv = 0.f;
-            if (ok) sv = p.sg[(rn % p.b_inner) * p.t_len + p.t];
+            if (ok) sv = p.sg[(rn % (uint32_t)p.b_inner) * (uint32_t)p.t_len + (uint32_t)p.t];    // (32-bit: a 64-bit % is a call)
 #pragma unroll
-            for (int c = 0; c < kMaxC; ++c) dst[c] = (ok && c < p.c_in) ? p.xo[(rn * p.t_len + p.t) * p.c_in + c] * sv : 0.f;
+            for (int c = 0; c < kMaxC; ++c)
+                dst[c] = (c < kC && ok && (CIN == 1 || c < p.c_in)) ? p.xo[((int64_t)rn * p.t_len + p.t) * p.c_in + c] * sv : 0.f;
         };
 #pragma unroll
         for (int j = 0; j < 4; ++j) load_c4((int)blockIdx.x, j);
@@ -328,8 +333,8 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                     float po = fmaf(__uint_as_float(v[4 * u + 3]), -1.4426950408889634f, bv.w);
                     if (l0) {
 #pragma unroll
-                        for (int c = 0; c < kMaxC; ++c)
-                            if (c < p.c_in) {
+                        for (int c = 0; c < kC; ++c)
+                            if (CIN == 1 || c < p.c_in) {
                                 const float4 wv = *reinterpret_cast<const float4*>(&tail->wih[c * kGateCols + col]);
                                 pi = fmaf(xs[c], wv.x, pi); pf = fmaf(xs[c], wv.y, pf);
                                 pg = fmaf(xs[c], wv.z, pg); po = fmaf(xs[c], wv.w, po);
@@ -477,8 +482,10 @@ struct Bwd16Params {
     int n_tiles;
 };
 
-template <int PLANES, bool L0>
+template <int PLANES, int CIN>                                  // CIN: see lstm16_fwd_kernel
 __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_constant__ Bwd16Params p) {
+    constexpr bool L0 = CIN > 0;
+    constexpr int kC = (CIN == 1) ? 1 : kMaxC;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round trip would make every access through
     // `smem` a generic LD/ST/ATOM instead of LDS/STS/ATOMS: ncu showed the bias loads as long-scoreboard stalls)
@@ -847,10 +854,10 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             const bool valid = r < rows32;
             if (L0) {
                 float sv = 0.f;
-                if (valid) sv = p.sg[((int64_t)r % p.b_inner) * p.t_len + p.t];
+                if (valid) sv = p.sg[(r % (uint32_t)p.b_inner) * (uint32_t)p.t_len + (uint32_t)p.t];      // (32-bit: a 64-bit % is a call)
 #pragma unroll
                 for (int c = 0; c < kMaxC; ++c) {
-                    xraw[c] = (valid && c < p.c_in) ? p.xo[((int64_t)r * p.t_len + p.t) * p.c_in + c] : 0.f;
+                    xraw[c] = (c < kC && valid && (CIN == 1 || c < p.c_in)) ? p.xo[((int64_t)r * p.t_len + p.t) * p.c_in + c] : 0.f;
                     xs[c] = xraw[c] * sv;
                     dxs[c] = 0.f;
                 }
@@ -905,8 +912,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     float po = fmaf(__uint_as_float(v[4 * u + 3]), -1.4426950408889634f, bv.w);
                     if (L0) {
 #pragma unroll
-                        for (int cc = 0; cc < kMaxC; ++cc)
-                            if (cc < p.c_in) {
+                        for (int cc = 0; cc < kC; ++cc)
+                            if (CIN == 1 || cc < p.c_in) {
                                 const float4 wv = *reinterpret_cast<const float4*>(&tail->wih[cc * kGateCols + col]);
                                 pi = fmaf(xs[cc], wv.x, pi); pf = fmaf(xs[cc], wv.y, pf);
                                 pg = fmaf(xs[cc], wv.z, pg); po = fmaf(xs[cc], wv.w, po);
@@ -924,8 +931,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     dcn[u] = dcv * gf;
                     if (L0) {
 #pragma unroll
-                        for (int cc = 0; cc < kMaxC; ++cc)
-                            if (cc < p.c_in) {
+                        for (int cc = 0; cc < kC; ++cc)
+                            if (CIN == 1 || cc < p.c_in) {
                                 // W_ih is stored pre-scaled: undo -log2(e) (and the g gate's extra factor 2)
                                 const float4 wv = *reinterpret_cast<const float4*>(&tail->wih[cc * kGateCols + col]);
                                 dxs[cc] = fmaf(da[4 * u] * wv.x + da[4 * u + 1] * wv.y + 0.5f * (da[4 * u + 2] * wv.z) + da[4 * u + 3] * wv.w,
@@ -962,8 +969,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 // gate adjoint: d s[b, t] += sum_c dxmod[r, c] * xo[r, t, c]   (STMGCN.py:44)
                 float contrib = 0.f;
 #pragma unroll
-                for (int cc = 0; cc < kMaxC; ++cc) contrib += dxs[cc] * xraw[cc];
-                const int64_t b = (int64_t)r % p.b_inner;
+                for (int cc = 0; cc < kC; ++cc) contrib += dxs[cc] * xraw[cc];
+                const int64_t b = (int64_t)(r % (uint32_t)p.b_inner);
                 if (p.b_inner <= kBSgMax) atomicAdd(&tail->s_ds[b], contrib);
                 else atomicAdd(&p.d_s[b * p.t_len + p.t], contrib);
             }
@@ -1081,6 +1088,18 @@ bool make_plane_map(CUtensorMap* map, const void* base, int64_t rows, int64_t sl
 
 static int32_t set_smem_attr(const void* fn, size_t bytes) { return ensure_dyn_smem(fn, bytes); }
 
+// kernel variant for (planes, cin): cin = 0 (not layer 0), 1 (layer 0, one input channel), kMaxC (layer 0, runtime count)
+using FwdFn = void (*)(const Fwd16Params);
+using BwdFn = void (*)(const Bwd16Params);
+static FwdFn fwd_kernel_for(int planes, int cin) {
+    if (planes == 2) return cin == 0 ? lstm16_fwd_kernel<2, 0> : (cin == 1 ? lstm16_fwd_kernel<2, 1> : lstm16_fwd_kernel<2, kMaxC>);
+    return cin == 0 ? lstm16_fwd_kernel<1, 0> : (cin == 1 ? lstm16_fwd_kernel<1, 1> : lstm16_fwd_kernel<1, kMaxC>);
+}
+static BwdFn bwd_kernel_for(int planes, int cin) {
+    if (planes == 2) return cin == 0 ? lstm16_bwd_kernel<2, 0> : (cin == 1 ? lstm16_bwd_kernel<2, 1> : lstm16_bwd_kernel<2, kMaxC>);
+    return cin == 0 ? lstm16_bwd_kernel<1, 0> : (cin == 1 ? lstm16_bwd_kernel<1, 1> : lstm16_bwd_kernel<1, kMaxC>);
+}
+
 }  // namespace stmgcn
 
 extern "C" int32_t stmgcn_lstm16_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
@@ -1109,8 +1128,9 @@ extern "C" int32_t stmgcn_lstm16_step_fwd(int32_t t, int32_t t_len, int32_t n_la
     const int64_t rows_pad = (int64_t)n_tiles * kTileM;
     const int64_t plane_elems = rows * kHid;                       // bf16 elements per plane
     const int64_t cslice = rows_pad * kHid;
-    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_fwd_kernel<2, true> : (const void*)lstm16_fwd_kernel<1, true>, kFSmem)) return rc;
-    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_fwd_kernel<2, false> : (const void*)lstm16_fwd_kernel<1, false>, kFSmem)) return rc;
+    const FwdFn fn0 = fwd_kernel_for(planes, c_in == 1 ? 1 : kMaxC), fn1 = fwd_kernel_for(planes, 0);
+    if (int32_t rc = set_smem_attr((const void*)fn0, kFSmem)) return rc;
+    if (int32_t rc = set_smem_attr((const void*)fn1, kFSmem)) return rc;
     CUtensorMap hp_map, h0_map;
     STMGCN_REQUIRE(make_plane_map(&hp_map, hp, rows, (int64_t)n_layers * t_len * planes), STMGCN_ERR_STATE,
                    "lstm16_step_fwd: cuTensorMapEncodeTiled failed (hp)");
@@ -1161,13 +1181,7 @@ extern "C" int32_t stmgcn_lstm16_step_fwd(int32_t t, int32_t t_len, int32_t n_la
         }
         p.rows = rows;
         p.n_tiles = n_tiles;
-        if (planes == 2) {
-            if (l == 0) lstm16_fwd_kernel<2, true><<<grid, kFThreads, kFSmem, st>>>(p);
-            else lstm16_fwd_kernel<2, false><<<grid, kFThreads, kFSmem, st>>>(p);
-        } else {
-            if (l == 0) lstm16_fwd_kernel<1, true><<<grid, kFThreads, kFSmem, st>>>(p);
-            else lstm16_fwd_kernel<1, false><<<grid, kFThreads, kFSmem, st>>>(p);
-        }
+        (l == 0 ? fn0 : fn1)<<<grid, kFThreads, kFSmem, st>>>(p);
         count_launch();
         if (int32_t rc = check_launch("lstm16_fwd")) return rc;
     }
@@ -1195,8 +1209,9 @@ extern "C" int32_t stmgcn_lstm16_step_bwd(int32_t t, int32_t t_len, int32_t n_la
     cudaStream_t st = (cudaStream_t)stream;
     const int n_tiles = (int)ceil_div(rows, kTileM);
     const int64_t cslice = (int64_t)n_tiles * kTileM * kHid;
-    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_bwd_kernel<2, true> : (const void*)lstm16_bwd_kernel<1, true>, kBSmem)) return rc;
-    if (int32_t rc = set_smem_attr(planes == 2 ? (const void*)lstm16_bwd_kernel<2, false> : (const void*)lstm16_bwd_kernel<1, false>, kBSmem)) return rc;
+    const BwdFn fn0 = bwd_kernel_for(planes, c_in == 1 ? 1 : kMaxC), fn1 = bwd_kernel_for(planes, 0);
+    if (int32_t rc = set_smem_attr((const void*)fn0, kBSmem)) return rc;
+    if (int32_t rc = set_smem_attr((const void*)fn1, kBSmem)) return rc;
     CUtensorMap hp_map, h0_map;
     STMGCN_REQUIRE(make_plane_map(&hp_map, hp, rows, (int64_t)n_layers * t_len * planes), STMGCN_ERR_STATE,
                    "lstm16_step_bwd: cuTensorMapEncodeTiled failed (hp)");
@@ -1254,13 +1269,7 @@ extern "C" int32_t stmgcn_lstm16_step_bwd(int32_t t, int32_t t_len, int32_t n_la
         }
         p.rows = rows;
         p.n_tiles = n_tiles;
-        if (planes == 2) {
-            if (l == 0) lstm16_bwd_kernel<2, true><<<grid, kBThreads, kBSmem, st>>>(p);
-            else lstm16_bwd_kernel<2, false><<<grid, kBThreads, kBSmem, st>>>(p);
-        } else {
-            if (l == 0) lstm16_bwd_kernel<1, true><<<grid, kBThreads, kBSmem, st>>>(p);
-            else lstm16_bwd_kernel<1, false><<<grid, kBThreads, kBSmem, st>>>(p);
-        }
+        (l == 0 ? fn0 : fn1)<<<grid, kBThreads, kBSmem, st>>>(p);
         count_launch();
         if (int32_t rc = check_launch("lstm16_bwd")) return rc;
     }
