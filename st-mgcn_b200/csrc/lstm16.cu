@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
         // reloaded at once with the NEXT tile's values, so the loads are in flight for most of a tile (loading all 16 at the
         // end of a tile exposed the full DRAM latency at the top of the next one: ncu showed 21 % of the samples there)
         float cpv[16];
-        float xs[kMaxC], xs_next[kMaxC];
+        float xs[kMaxC], xs_next[kMaxC], sv_next = 0.f;    // xs_next: raw x of the next tile; scaled by sv_next at the swap
         // 32-bit element offsets (rows <= 2^25 is checked on the host): 64-bit address pairs cost registers, and the few
         // that spilled were re-read from local memory in the tile loop at full L1-miss latency (ncu: 18 % of the samples)
         const uint32_t row_in_tile = (uint32_t)(q * 32 + lane);
@@ -284,18 +284,24 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                 v = *reinterpret_cast<const float4*>(p.c_prev + ((uint32_t)tile_n * 8192u + thr_c + (uint32_t)j * 512u));
             cpv[4 * j] = v.x; cpv[4 * j + 1] = v.y; cpv[4 * j + 2] = v.z; cpv[4 * j + 3] = v.w;
         };
-        auto load_xs = [&](int tile_n, float (&dst)[kMaxC]) {
+        // loads only: the product x * s is formed when the tile starts (multiplying here waited for the loads on the spot:
+        // 14 % of the layer-0 kernel's stall samples)
+        auto load_xs = [&](int tile_n) {
             const uint32_t rn = (uint32_t)tile_n * kTileM + row_in_tile;
             const bool ok = tile_n < p.n_tiles && rn < rows32;
-            float sv = 0.f;
-            if (ok) sv = p.sg[(rn % (uint32_t)p.b_inner) * (uint32_t)p.t_len + (uint32_t)p.t];    // (32-bit: a 64-bit % is a call)
+            sv_next = 0.f;
+            if (ok) sv_next = p.sg[(rn % (uint32_t)p.b_inner) * (uint32_t)p.t_len + (uint32_t)p.t];    // (32-bit: a 64-bit % is a call)
 #pragma unroll
             for (int c = 0; c < kMaxC; ++c)
-                dst[c] = (c < kC && ok && (CIN == 1 || c < p.c_in)) ? p.xo[((int64_t)rn * p.t_len + p.t) * p.c_in + c] * sv : 0.f;
+                xs_next[c] = (c < kC && ok && (CIN == 1 || c < p.c_in)) ? p.xo[((int64_t)rn * p.t_len + p.t) * p.c_in + c] : 0.f;
         };
 #pragma unroll
         for (int j = 0; j < 4; ++j) load_c4((int)blockIdx.x, j);
-        if (l0) load_xs((int)blockIdx.x, xs);
+        if (l0) {
+            load_xs((int)blockIdx.x);
+#pragma unroll
+            for (int c = 0; c < kMaxC; ++c) xs[c] = xs_next[c] * sv_next;
+        }
         const int gstep = (int)gridDim.x;
         int tile = (int)blockIdx.x;                // carried in a register: re-reading %ctaid every tile is a long-scoreboard stall
         for (int i = 0; i < my_tiles; ++i, tile += gstep) {
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                         *reinterpret_cast<float4*>(p.h_f32 + (r * (uint32_t)kHid + (uint32_t)unit0)) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                 }
                 load_c4(tile + gstep, pc);                      // this piece's registers are free: next tile's values
-                if (l0 && pc == 0) load_xs(tile + gstep, xs_next);
+                if (l0 && pc == 0) load_xs(tile + gstep);
             }
             if (p.nseg > 0) {          // all TMEM reads of this accumulator are done (one mbarrier arrival per warp: 512
                 tc_fence_before();     // per-thread arrivals are 512 serialised shared-memory atomics per tile)
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
             }
             if (l0) {
 #pragma unroll
-                for (int c = 0; c < kMaxC; ++c) xs[c] = xs_next[c];
+                for (int c = 0; c < kMaxC; ++c) xs[c] = xs_next[c] * sv_next;
             }
         }
         TC_PROF_FLUSH(2, tid == 0)
@@ -806,6 +812,21 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         const uint32_t row_in_tile = (uint32_t)(q * 32 + lane);
         const uint32_t rows32 = (uint32_t)p.rows;       // (rows <= 2^25 is checked on the host: 32-bit element offsets)
         const uint32_t thr_off = row_in_tile * 4u + (uint32_t)part * 512u;
+        float xraw_next[kMaxC], sv_next = 0.f;      // layer 0: x and gate value of the next tile, loaded a chunk ahead
+        // layer 0: when b_inner divides the tile height, a thread's row belongs to the same window b in every tile: its share
+        // of d_s is summed in a register and added once (one shared-memory float atomic = a CAS loop; 16 per address and tile
+        // were 6 % of the layer-0 kernel's stall samples)
+        const bool ds_fixed = L0 && (kTileM % (uint32_t)p.b_inner) == 0u;
+        float ds_acc = 0.f;
+        auto load_x = [&](int tile_n) {
+            const uint32_t rn = (uint32_t)tile_n * kTileM + row_in_tile;
+            const bool ok = tile_n < p.n_tiles && rn < rows32;
+            sv_next = 0.f;
+            if (ok) sv_next = p.sg[(rn % (uint32_t)p.b_inner) * (uint32_t)p.t_len + (uint32_t)p.t];      // (32-bit: a 64-bit % is a call)
+#pragma unroll
+            for (int c = 0; c < kMaxC; ++c)
+                xraw_next[c] = (c < kC && ok && (CIN == 1 || c < p.c_in)) ? p.xo[((int64_t)rn * p.t_len + p.t) * p.c_in + c] : 0.f;
+        };
         auto load_raw = [&](int tile, int c, Raw& rw) {
             const uint32_t r = (uint32_t)tile * kTileM + row_in_tile;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -849,16 +870,15 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         const int gstep = (int)gridDim.x;
         int tile = (int)blockIdx.x;
         load_raw(tile, 0, nxt);
+        if (L0) load_x(tile);
         for (int i = 0; i < my_tiles; ++i, tile += gstep) {
             const uint32_t r = (uint32_t)tile * kTileM + row_in_tile;
             const bool valid = r < rows32;
             if (L0) {
-                float sv = 0.f;
-                if (valid) sv = p.sg[(r % (uint32_t)p.b_inner) * (uint32_t)p.t_len + (uint32_t)p.t];      // (32-bit: a 64-bit % is a call)
 #pragma unroll
                 for (int c = 0; c < kMaxC; ++c) {
-                    xraw[c] = (c < kC && valid && (CIN == 1 || c < p.c_in)) ? p.xo[((int64_t)r * p.t_len + p.t) * p.c_in + c] : 0.f;
-                    xs[c] = xraw[c] * sv;
+                    xraw[c] = xraw_next[c];
+                    xs[c] = xraw[c] * sv_next;
                     dxs[c] = 0.f;
                 }
             }
@@ -960,7 +980,10 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 // next chunk's inputs: issued AFTER the proxy fence -- fence.proxy.async implies MEMBAR.ALL.CTA, which waits for
                 // every outstanding load of the thread, so a prefetch issued before it is simply waited for at the fence
                 if (c < 3) load_raw(tile, c + 1, nxt);
-                else load_raw(tile + gstep, 0, nxt);
+                else {
+                    load_raw(tile + gstep, 0, nxt);
+                    if (L0) load_x(tile + gstep);
+                }
                 if (valid)
                     *reinterpret_cast<float4*>(p.dc + ((uint32_t)tile * 8192u + (uint32_t)c * 2048u + thr_off)) =
                         make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
@@ -970,11 +993,16 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 float contrib = 0.f;
 #pragma unroll
                 for (int cc = 0; cc < kC; ++cc) contrib += dxs[cc] * xraw[cc];
-                const int64_t b = (int64_t)(r % (uint32_t)p.b_inner);
-                if (p.b_inner <= kBSgMax) atomicAdd(&tail->s_ds[b], contrib);
-                else atomicAdd(&p.d_s[b * p.t_len + p.t], contrib);
+                if (ds_fixed) {
+                    ds_acc += contrib;
+                } else {
+                    const int64_t b = (int64_t)(r % (uint32_t)p.b_inner);
+                    if (p.b_inner <= kBSgMax) atomicAdd(&tail->s_ds[b], contrib);
+                    else atomicAdd(&p.d_s[b * p.t_len + p.t], contrib);
+                }
             }
         }
+        if (ds_fixed && my_tiles > 0) atomicAdd(&tail->s_ds[row_in_tile % (uint32_t)p.b_inner], ds_acc);   // (b_inner <= 128 <= kBSgMax)
         if (my_tiles > 0 && p.nseg > 0) drain(my_tiles - 1, tile - gstep);
         TC_PROF_FLUSH(3, tid == 0)
         // ---- weight-gradient accumulator -> this CTA's scratch slice (register layout: [part][piece][vec][row m][4]) ----
