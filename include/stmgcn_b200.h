@@ -76,6 +76,15 @@ int32_t stmgcn_cheb_spmm_step(const stmgcn_graph_t* g, int32_t transpose, float 
                               float beta, const float* z, float gamma, const float* u, float* y,
                               int64_t f_total, void* stream);
 
+/* The same step with the GATHERED operand read from a bf16 copy (the bf16-arithmetic mode of the bf16-quoted
+ * configurations: the kernel's time is its gather volume): x16 (N, f_total) bf16; z, u, y stay fp32; y16 (nullable) receives
+ * the bf16 copy of y for the next step.  f_total must be a multiple of 8.  stmgcn_to_bf16 makes the first copy
+ * (count elements, a multiple of 8). */
+int32_t stmgcn_cheb_spmm_step16(const stmgcn_graph_t* g, int32_t transpose, float alpha, const void* x16,
+                                float beta, const float* z, float gamma, const float* u, float* y, void* y16,
+                                int64_t f_total, void* stream);
+int32_t stmgcn_to_bf16(const float* x, void* y16, int64_t count, void* stream);
+
 /* ---- layout: obs (B,T,N,C) -> node-major (STMGCN.py:36,39 sum over C + permute; :47 row order) ----
  * xo: (N,B,T,C) copy of obs;  xt: (N,B,T) = sum_c obs.  xo may be NULL when C == 1 (xt is then xo). */
 int32_t stmgcn_obs_to_node_major(const float* obs, float* xo, float* xt, int64_t b, int64_t t,

@@ -29,6 +29,8 @@ SIGNATURES = [
     ("stmgcn_graph_nnz", c_int64, [_P]),
     ("stmgcn_graph_export", c_int32, [_P, c_int32, _P, _P, _P, _P]),
     ("stmgcn_cheb_spmm_step", c_int32, [_P, c_int32, c_float, _P, c_float, _P, c_float, _P, _P, c_int64, _P]),
+    ("stmgcn_cheb_spmm_step16", c_int32, [_P, c_int32, c_float, _P, c_float, _P, c_float, _P, _P, _P, c_int64, _P]),
+    ("stmgcn_to_bf16", c_int32, [_P, _P, c_int64, _P]),
     ("stmgcn_obs_to_node_major", c_int32, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, _P]),
     ("stmgcn_proj_fwd", c_int32, [_P, c_int64, c_int32, c_int64, c_int32, _P, _P, c_int32, c_int32, _P, _P,
                                   c_int64, _P, _P]),

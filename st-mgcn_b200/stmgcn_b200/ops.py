@@ -73,12 +73,41 @@ def spmm_step(g, transpose: bool, alpha: float, x: torch.Tensor, beta: float, z:
                                        y.data_ptr(), f_total, _stream()), "cheb_spmm_step")
 
 
-def cheb_stack_(sset: SupportSet, s: torch.Tensor) -> None:
-    """Fill ``s[1:]`` from ``s[0]``;  s: (Ks, N, B, p)."""
+def spmm_step16(g, transpose: bool, alpha: float, x16: torch.Tensor, beta: float, z: Optional[torch.Tensor],
+                gamma: float, u: Optional[torch.Tensor], y: torch.Tensor, y16: Optional[torch.Tensor]) -> None:
+    """:func:`spmm_step` with the gathered operand read from its bf16 copy ``x16``; writes the bf16 copy of ``y`` to ``y16``."""
+    f_total = y.numel() // g.n
+    _lib.check(L.stmgcn_cheb_spmm_step16(g.ptr, int(transpose), alpha, x16.data_ptr(), beta, _p(z), gamma, _p(u),
+                                         y.data_ptr(), _p(y16), f_total, _stream()), "cheb_spmm_step16")
+
+
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.check(L.stmgcn_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "to_bf16")
+    return y
+
+
+def _gather16(sset: SupportSet, x: torch.Tensor) -> bool:
+    """bf16 gather copies: only in the single-plane (bf16 arithmetic) mode, for the recurrence over one graph."""
+    return lstm_planes() == 1 and sset.mode == "cheb" and (x.numel() // sset.graphs[0].n) % 8 == 0 and x.numel() % 8 == 0
+
+
+def cheb_stack_(sset: SupportSet, s: torch.Tensor, gather16: bool = False) -> None:
+    """Fill ``s[1:]`` from ``s[0]``;  s: (Ks, N, B, p).  ``gather16``: allow bf16 gather copies (bf16-arithmetic mode only)."""
     ks = sset.ks
     if sset.mode == "cheb":
         if ks > 1:
             g = sset.graphs[0]
+            if gather16 and _gather16(sset, s[0]):
+                # bf16 mode: every step gathers from the bf16 copy of the previous term (half the gather volume)
+                src = to_bf16(s[0])
+                nxt = torch.empty_like(src) if ks > 2 else None
+                for k in range(1, ks):
+                    out16 = nxt if k < ks - 1 else None
+                    spmm_step16(g, False, 1.0 if k == 1 else 2.0, src, 0.0 if k == 1 else -1.0, None if k == 1 else s[k - 2],
+                                0.0, None, s[k], out16)
+                    src, nxt = out16, src
+                return
             spmm_step(g, False, 1.0, s[0], 0.0, None, 0.0, None, s[1])
             for k in range(2, ks):
                 spmm_step(g, False, 2.0, s[k - 1], -1.0, s[k - 2], 0.0, None, s[k])
@@ -94,11 +123,11 @@ def cheb_stack_generic(sset: SupportSet, x: torch.Tensor) -> torch.Tensor:
     return s
 
 
-def build_stack(sset: SupportSet, x: torch.Tensor) -> torch.Tensor:
+def build_stack(sset: SupportSet, x: torch.Tensor, gather16: bool = False) -> torch.Tensor:
     if sset.mode == "cheb":
         s = torch.empty((sset.ks,) + tuple(x.shape), device=x.device, dtype=torch.float32)
         s[0].copy_(x)
-        cheb_stack_(sset, s)
+        cheb_stack_(sset, s, gather16)
         return s
     return cheb_stack_generic(sset, x)
 
@@ -115,6 +144,9 @@ def adjoint_stack_(sset: SupportSet, u: torch.Tensor) -> torch.Tensor:
         g = sset.graphs[0]
         k_ord = ks - 1
         # b_K = U_K (in place).  b_k = U_k + 2 L^T b_{k+1} - b_{k+2}  written over U_k.
+        # (always fp32 gathers here, also in the bf16-arithmetic mode: rounding b_{k+1} to bf16 before every gather puts
+        # ~1.5e-2 into dX on the golden case -- the Clenshaw sum cancels -- and pushed one LSTM weight gradient to 2.2e-2,
+        # past the 2e-2 bar of that mode; measured.  The forward stack keeps its bf16 gather copies.)
         for k in range(k_ord - 1, 0, -1):
             z = u[k + 2] if k + 2 <= k_ord else None
             spmm_step(g, True, 2.0, u[k + 1], -1.0 if z is not None else 0.0, z, 1.0, u[k], u[k])
@@ -210,7 +242,11 @@ class ChebGCN(torch.autograd.Function):
         _require_cuda(x, w)
         x, w = _f32c(x), _f32c(w)
         bias_c = _f32c(bias) if bias is not None else None
-        s = build_stack(sset, x)
+        # bf16-arithmetic mode: the spatial recurrence (F = B*64 features per node: the step's large gather volume) reads its
+        # gathered operand from bf16 copies.  Not the temporal GCN (TemporalPool): its output feeds a global mean and the
+        # two-layer gate, whose parameter gradients are small differences of large sums -- with bf16 gathers there they
+        # moved by 2-3.6e-2 on the golden case (measured), past that mode's 2e-2 bar -- and its F = B*T rows are cheap.
+        s = build_stack(sset, x, gather16=True)
         need_grad = any(ctx.needs_input_grad)
         img_f, img_b = _proj_images(w, sset.ks, x.shape[2], need_grad)
         out = _proj_fwd(s, w, bias_c, act, None, x.shape[1], img_f)

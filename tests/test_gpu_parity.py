@@ -62,6 +62,26 @@ def test_spmm_step(n, f, transpose):
     assert_close(ud.cpu().numpy(), 2.0 * (op.astype(np.float64) @ x) - z + u, "spmm in-place", 1e-5)
 
 
+@pytest.mark.parametrize("n,f", [(64, 32), (97, 8), (300, 768), (128, 136)])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_spmm_step_with_bf16_gather_copy(n, f, transpose):
+    """stmgcn_cheb_spmm_step16 (bf16-arithmetic mode): the gathered operand is the bf16 copy, everything else fp32 -- equal
+    to the fp32 kernel run on the rounded operand; the bf16 copy of the result is the rounded result; u may alias y."""
+    from stmgcn_b200 import ops
+    from stmgcn_b200.graph import GraphHandle
+    g = GraphHandle.from_dense(torch.from_numpy(_rand_csr(n, 0.08, n + f)).to(DEV))
+    gen = torch.Generator().manual_seed(n + f)
+    x, z, u = (torch.randn(n, f, generator=gen).to(DEV) for _ in range(3))
+    x16 = ops.to_bf16(x)
+    assert torch.equal(x16, x.to(torch.bfloat16))
+    y_ref = torch.empty_like(x)
+    ops.spmm_step(g, transpose, 2.0, x16.float(), -1.0, z, 1.0, u, y_ref)
+    y, y16 = u.clone(), torch.empty_like(x16)
+    ops.spmm_step16(g, transpose, 2.0, x16, -1.0, z, 1.0, y, y, y16)              # u aliases y
+    assert_close(y.cpu().numpy(), y_ref.cpu().numpy(), "spmm16 vs fp32 kernel on the rounded operand", 1e-6)
+    assert torch.equal(y16, y.to(torch.bfloat16))
+
+
 @pytest.mark.parametrize("name", ["cfg1_ref", "ragged_ref", "cfg3_small_ref"])
 def test_model_matches_reference_golden(name):
     """Forward output, loss and EVERY parameter gradient vs vectors produced by the unmodified reference."""
@@ -367,8 +387,10 @@ def test_bf16_arithmetic_mode_within_the_reference_bf16_tolerance():
                          [O.laplacian_csr_from_supports(s) for s in supports], meta["k"] + 1, relu=False, dtype=np.float64)
     o_ref, _, g_ref = orc.loss_and_grads(blob["x"], blob["y"])
     e_out_s = assert_close(out_s.detach().cpu().numpy(), o_ref, "bf16 mode forward (smooth model)", 2e-2)
-    errs = {key: assert_close(p.grad.cpu().numpy(), g_ref[key], f"bf16 mode grad {key}", 2e-2)
-            for key, p in smooth.named_parameters()}
+    errs = {key: O.max_rel_err(p.grad.cpu().numpy(), g_ref[key]) for key, p in smooth.named_parameters()}
     print(f"bf16 arithmetic mode: forward error {e_out:.2e} (ReLU) / {e_out_s:.2e} (smooth); worst gradient error "
-          f"{max(errs.values()):.2e} ({max(errs, key=errs.get)}); tolerance 2e-2")
+          f"{max(errs.values()):.2e} ({max(errs, key=errs.get)}); tolerance 2e-2; all: "
+          + ", ".join(f"{k} {v:.1e}" for k, v in sorted(errs.items(), key=lambda kv: -kv[1])[:12]))
+    bad = {k: v for k, v in errs.items() if not v <= 2e-2}
+    assert not bad, f"bf16 mode gradients above 2e-2: {bad}"
     assert e_out > 1e-6, "the bf16 mode produced fp32-grade results: the single-pass path did not run"

@@ -26,3 +26,16 @@ torch.cuda.synchronize()
 alg = g.nnz * 8 + (w.n_regions + 1) * 4 + 3 * w.n_regions * f * 4
 us = e0.elapsed_time(e1) / 10 * 1e3
 print(json.dumps({"us_per_launch": us, "algorithmic_bytes": alg, "achieved_GBps": alg / us / 1e3, "nnz": g.nnz}))
+# the same launch with the gathered operand read from its bf16 copy (bf16-arithmetic mode), writing y and its bf16 copy
+x16, y16 = ops.to_bf16(x), torch.empty(x.shape, device=dev, dtype=torch.bfloat16)
+for _ in range(3):
+    ops.spmm_step16(g, False, 2.0, x16, -1.0, z, 0.0, None, y, y16)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(10):
+    ops.spmm_step16(g, False, 2.0, x16, -1.0, z, 0.0, None, y, y16)
+e1.record()
+torch.cuda.synchronize()
+alg16 = g.nnz * 8 + (w.n_regions + 1) * 4 + w.n_regions * f * (2 + 4 + 4 + 2)
+us16 = e0.elapsed_time(e1) / 10 * 1e3
+print(json.dumps({"bf16_gather_us_per_launch": us16, "algorithmic_bytes": alg16, "achieved_GBps": alg16 / us16 / 1e3}))
