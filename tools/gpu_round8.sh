@@ -9,7 +9,7 @@ run() { # name, args...
 import json, sys
 name = sys.argv[1]
 try:
-    d = json.load(open(f"gpurun_out/{name}.json"))
+    d = json.loads([l for l in open(f"gpurun_out/{name}.json").read().splitlines() if l.startswith("{")][-1])   # (NCCL may print a banner first)
     print(name, "ms/step", round(d["ms_per_step"], 2), "value", round(d["value"] / 1e6, 1), "M  e2e", round(d["e2e"]["value"] / 1e6, 1),
           "M  per-rank ms", [round(v, 2) for v in d["per_rank_ms_per_step"]], "allreduce us", d["allreduce_us"], d["loss_check"]["ok"], d["clocks"])
 except Exception as e:
