@@ -225,13 +225,17 @@ __global__ void __launch_bounds__(kFThreads, 1) lstm16_fwd_kernel(const __grid_c
                         tc_fence_after();
                         if (leader) {
                             const uint64_t a_d = desc16_k(smem_u32(stages + (size_t)stg * kATileBytes));
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                mma_bf16(d_tmem, a_d + (uint64_t)(2 * kk), w_hi + (uint64_t)(2 * kk), idesc, (s > 0 || kk > 0) ? 1u : 0u);
                             if (PLANES == 2) {
+                                // per k-step: A_hi . W_hi keeps A in the collector, A_hi . W_lo re-uses it (one A read, not two)
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    mma_bf16_keep_a(d_tmem, a_d + (uint64_t)(2 * kk), w_hi + (uint64_t)(2 * kk), idesc, (s > 0 || kk > 0) ? 1u : 0u);
+                                    mma_bf16_reuse_a(d_tmem, a_d + (uint64_t)(2 * kk), w_lo + (uint64_t)(2 * kk), idesc, 1u);
+                                }
+                            } else {
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk)
-                                    mma_bf16(d_tmem, a_d + (uint64_t)(2 * kk), w_lo + (uint64_t)(2 * kk), idesc, 1u);
+                                    mma_bf16(d_tmem, a_d + (uint64_t)(2 * kk), w_hi + (uint64_t)(2 * kk), idesc, (s > 0 || kk > 0) ? 1u : 0u);
                             }
                             mma_commit(&tail->empty[stg]);
                         }
@@ -435,7 +439,7 @@ __global__ void lstm16_pack_kernel(const float* __restrict__ w_ih, const float* 
 // per layer and writes nn.LSTM-native gradients.
 // The kernel is bound by the L1 / shared-memory data pipe (ncu: 94 %: tensor-core operand reads 61 % + LSU 33 %).
 constexpr int kBCompWarps = 16;
-constexpr int kBThreads = (kBCompWarps + 4) * 32;       // + three MMA-issuing warps + producer warp
+constexpr int kBThreads = (kBCompWarps + 2) * 32;       // + MMA-issuing warp + producer warp
 constexpr int kBWStages = 2;                            // two single-buffered slots: the recompute's and the data gradient's copy
 constexpr int kBWChunkTile = 64 * 128;                  // [64 gate cols][64 k] bf16 = 8 KB
 constexpr int kBWStageBytes = 4 * kBWChunkTile;         // (seg0 hi | seg0 lo | seg1 hi | seg1 lo) = 32 KB
@@ -508,7 +512,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     const int warp = tid >> 5;
     const int lane = tid & 31;
     constexpr int kMmaWarp = kBCompWarps;
-    constexpr int kProdWarp = kBCompWarps + 3;
+    constexpr int kProdWarp = kBCompWarps + 1;
     constexpr int kCompThreads = kBCompWarps * 32;
     // TMEM columns: weight grad (256) | data grad (128) | recompute (64, single buffer: the compute warps hold it only for
     // the TMEM -> register copy at the start of a chunk) | bias grad (4 chunks x 16)
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         mbar_init(&tail->r_full, 1);
         mbar_init(&tail->r_empty, kBCompWarps);                // one arrival per compute warp
         mbar_init(&tail->d_full, kBCompWarps);
-        mbar_init(&tail->d_empty, 2);                          // weight-gradient warp + data-gradient warp
+        mbar_init(&tail->d_empty, 1);
         mbar_init(&tail->g_full, 1);
         mbar_init(&tail->g_empty, kBCompWarps);
         mbar_init(&tail->done, 1);
@@ -632,171 +636,168 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             }
         }
         TC_PROF_FLUSH(5, leader)
-    } else if (warp >= kMmaWarp && warp < kProdWarp) {
-        // ===================== three MMA issuers: recompute (R) | weight gradient (W) | data gradient (D) =====================
-        // A tile needs ~240 tcgen05.mma instructions; issued by ONE thread they cost ~90 cycles apiece (ptxas moves every
-        // descriptor from vector to uniform registers around each UTCHMMA: measured 66 % of that warp's lifetime, 21 k cycles
-        // per tile against 9.2 k cycles of tensor-pipe work).  The three GEMMs write disjoint TMEM accumulators, so each gets
-        // its own issuing warp; tcgen05.commit tracks the issuing thread's MMAs, so every hand-off barrier is committed by
-        // the warp whose MMAs it guards (the dA buffer is released by W and D together: count 2).
-        // Everything that does not change is hoisted into 64-bit descriptor constants; a k-step is one add on the
-        // descriptor's address field (encoded address = bytes >> 4; all operands live below 256 KB: no carry).
+    } else if (warp == kMmaWarp) {
+        // ===================== the MMA issuer: recompute (R) | weight gradient (W) | bias gradient | data gradient (D) =====================
+        // ONE thread issues every tcgen05.mma of the CTA, in the order the work becomes ready:
+        //     R_{g+1} (hi passes [+ lo pass])  ->  W_g lo pass, D_g, W_g hi passes, bias gradient  ->  [tile boundary: R_{g+1} lo pass]
+        // R_{g+1} is released when the compute warps have copied G_g out of TMEM (start of chunk-time g), W_g / D_g when dA_g is in
+        // shared memory (its end).  (An earlier version used three issuing warps because an issue cost ~90 cycles -- that was the
+        // ELECT / BRA.U.ANY loop ptxas wraps around `lane == 0`-guarded UTCHMMAs, gone with elect.sync.)  A single in-order issuer
+        // is what makes the A-operand collector usable: in the 3xBF16 scheme the products A_hi.B_hi and A_hi.B_lo share A, so
+        // the second MMA of each pair takes A from the tensor core's collector buffer instead of re-reading 4 KB of shared memory
+        // -- the kernel is bound by the shared-memory data pipe (ncu: 94 %, 61 % of it tensor-core operand reads).
+        // Everything that does not change is hoisted into 64-bit descriptor constants; a k-step is one add on the descriptor's
+        // address field (encoded address = bytes >> 4; all operands live below 256 KB: no carry).
         TC_PROF_DECL
         const bool leader = elect_one_sync();
         constexpr uint32_t idesc_rc = idesc_bf16(kTileM, 64);              // recompute: A K-major, B K-major, N = 64
         constexpr uint32_t idesc_wg = idesc_bf16(kTileM, 64, 1, 1);        // weight gradient: both MN-major, M = kd (128), N = 64
+        constexpr uint32_t idesc_db = idesc_bf16(kTileM, 16, 1, 0);        // bias gradient: A = dA^T (hi | lo atoms), B = ones
         const uint32_t idesc_dg = idesc_bf16(kTileM, 64 * (p.nseg > 0 ? p.nseg : 1), 0, 1);   // data gradient: B MN-major, N = 64 * nseg
         const uint32_t a_u = smem_u32(a_sm), w_u = smem_u32(w_sm), da_u = smem_u32(da_sm);
         constexpr uint64_t kStepK = 2;                                     // K-major: 16 bf16 = 32 bytes
         constexpr uint64_t kStepMN = 2048 >> 4;                            // MN-major: 16 rows of 128 bytes
         constexpr uint64_t kTileEnc = kATileBytes >> 4, kChunkEnc = kBWChunkTile >> 4, kStageEnc = kBWStageBytes >> 4;
         const int nseg = p.nseg;
-        const int role = warp - kMmaWarp;                                  // 0: R, 1: W, 2: D
-        if (role == 0) {
-            // ---- R: G_c[128 x 64] = [h_below | h_prev] . Wp[:, chunk c] ----
-            const uint64_t rc_a = desc16_k(a_u);                           // hi: + (buffer*2 + s) * kTileEnc; lo: + (4 + s) * kTileEnc
-            const uint64_t rc_b = desc16_k(w_u);                           // + stage * kStageEnc + (s*2 + plane) * kChunkEnc
-            const uint32_t t_rc = tmem_base + kRcCol;
-            uint32_t wc = 0;
-            if (nseg > 0) {
-                for (int i = 0; i < my_tiles; ++i) {
-                    const int ab = i & 1;
-                    mbar_wait_p(&tail->ahi_full[ab], (uint32_t)(i >> 1) & 1, 3);
-                    for (int c = 0; c < 4; ++c, ++wc) {
-                        mbar_wait_p(&tail->w_full[0], wc & 1, 0);
-                        mbar_wait_p(&tail->r_empty, (wc & 1) ^ 1, 2);
-                        tc_fence_after();
-                        const uint32_t d = t_rc;
-                        const uint64_t bs = rc_b;                   // buffer 0: the recompute's copy of the chunk
-                        if (leader) {                               // passes on the hi planes (double-buffered: already here)
+        const uint64_t rc_a = desc16_k(a_u);                               // hi: + (buffer*2 + s) * kTileEnc; lo: + (4 + s) * kTileEnc
+        const uint64_t rc_b = desc16_k(w_u);                               // buffer 0 (the recompute's copy): + (s*2 + plane) * kChunkEnc
+        const uint64_t wg_hi0 = desc16_mn(a_u + wg_a0 * kATileBytes, wg_lbo);              // hi buffer 0; buffer 1: + 2 * kTileEnc
+        const uint64_t wg_lo = desc16_mn(a_u + (4 + wg_a0) * kATileBytes, wg_lbo);         // lo planes
+        const uint64_t wg_b = desc16_mn(da_u, kATileBytes);                                  // dA hi; lo: + kTileEnc
+        const uint64_t db_b = desc16_k(smem_u32(tail->ones));
+        const uint64_t dg_a = desc16_k(da_u);                              // dA hi; lo: + kTileEnc
+        const uint64_t dg_b = desc16_mn(w_u, 2 * kBWChunkTile) + kStageEnc;   // buffer 1 (the data gradient's copy) (+ kChunkEnc: lo plane)
+        const uint32_t t_rc = tmem_base + kRcCol, t_wg = tmem_base + kWgCol, t_db = tmem_base + kDbCol, t_dg = tmem_base + kDgCol;
+        const bool a_sync = nseg > 0 || L0;          // someone waits for the A buffers (producer and / or the aux-tile writers)
+        const uint32_t total = 4u * (uint32_t)my_tiles;
+
+        // hi-plane passes of the recompute of chunk wc (tile wc >> 2): G = A_hi . (W_hi + W_lo)
+        auto issue_r_hi = [&](uint32_t wc) {
+            const int ab = (int)((wc >> 2) & 1);
 #pragma unroll
-                            for (int s = 0; s < 2; ++s) {
-                                if (s < nseg) {
-                                    const uint64_t a_hi = rc_a + (uint64_t)(ab * 2 + s) * kTileEnc;
-                                    const uint64_t b_hi = bs + (uint64_t)(s * 2) * kChunkEnc, b_lo = b_hi + kChunkEnc;
+            for (int s = 0; s < 2; ++s) {
+                if (s < nseg) {
+                    const uint64_t a_hi = rc_a + (uint64_t)(ab * 2 + s) * kTileEnc;
+                    const uint64_t b_hi = rc_b + (uint64_t)(s * 2) * kChunkEnc, b_lo = b_hi + kChunkEnc;
 #pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk)
-                                        mma_bf16(d, a_hi + kk * kStepK, b_hi + kk * kStepK, idesc_rc, (s > 0 || kk > 0) ? 1u : 0u);
-                                    if (PLANES == 2) {
-#pragma unroll
-                                        for (int kk = 0; kk < 4; ++kk) mma_bf16(d, a_hi + kk * kStepK, b_lo + kk * kStepK, idesc_rc, 1u);
-                                    }
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        if (PLANES == 2) {                             // pass on the lo planes (single buffer: may still be loading)
-                            if (c == 0) {
-                                mbar_wait_p(&tail->alo_full, (uint32_t)i & 1, 3);
-                                tc_fence_after();
-                            }
-                            if (leader) {
-#pragma unroll
-                                for (int s = 0; s < 2; ++s) {
-                                    if (s < nseg) {
-                                        const uint64_t a_lo = rc_a + (uint64_t)(4 + s) * kTileEnc;
-                                        const uint64_t b_hi = bs + (uint64_t)(s * 2) * kChunkEnc;
-#pragma unroll
-                                        for (int kk = 0; kk < 4; ++kk) mma_bf16(d, a_lo + kk * kStepK, b_hi + kk * kStepK, idesc_rc, 1u);
-                                    }
-                                }
-                            }
-                        }
-                        if (leader) {
-                            mma_commit(&tail->w_empty[0]);
-                            mma_commit(&tail->r_full);
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-            TC_PROF_FLUSH(4, leader)
-        } else if (role == 1) {
-            // ---- W: dWp[:, chunk c] += A'^T . dA_c   (M = kd 128, N = 64, K = 128 rows); one accumulator for the launch ----
-            // pass order: the lo-plane pass FIRST, so that the tile's last group releases the single lo buffer a.s.a.p.
-            const uint64_t wg_hi0 = desc16_mn(a_u + wg_a0 * kATileBytes, wg_lbo);              // hi buffer 0; buffer 1: + 2 * kTileEnc
-            const uint64_t wg_lo = desc16_mn(a_u + (4 + wg_a0) * kATileBytes, wg_lbo);         // lo planes
-            const uint64_t wg_b = desc16_mn(da_u, kATileBytes);                                  // dA hi; lo: + kTileEnc
-            const uint32_t t_wg = tmem_base + kWgCol;
-            // bias gradient on the tensor pipe: D[128 x 16] += dA_c^T (MN-major A, M = 64 columns of the hi plane | 64 of the
-            // lo plane: the two planes are the two 64-element atoms, LBO = one tile) . ones[K = 16 rows][16].  Lane m < 64 of
-            // the accumulator holds sum_rows hi(dA)[:, m], lane 64 + m the lo plane's sum; all 16 columns are equal.  (The
-            // shuffle butterfly this replaces was 21 % of the compute warps' stall samples.)
-            constexpr uint32_t idesc_db = idesc_bf16(kTileM, 16, 1, 0);
-            const uint64_t db_b = desc16_k(smem_u32(tail->ones));
-            const uint32_t t_db = tmem_base + kDbCol;
-            const bool a_sync = nseg > 0 || L0;      // someone waits for the A buffers (producer and / or the aux-tile writers)
-            uint32_t dcount = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                const uint64_t wg_hi = wg_hi0 + (uint64_t)((i & 1) * 2) * kTileEnc;
-                for (int c = 0; c < 4; ++c, ++dcount) {
-                    mbar_wait_p(&tail->d_full, dcount & 1, 1);
-                    tc_fence_after();
-                    if (leader) {
-                        const uint32_t d_wg = t_wg + (uint32_t)c * 64;
-                        const uint32_t acc0 = (i > 0) ? 1u : 0u;
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t acc = (s > 0 || kk > 0) ? 1u : 0u;
                         if (PLANES == 2) {
-                            mma_bf16(d_wg, wg_lo, wg_b, idesc_wg, acc0);
-#pragma unroll
-                            for (int ks = 1; ks < 8; ++ks) mma_bf16(d_wg, wg_lo + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, 1u);
-                            if (c == 3 && a_sync) mma_commit(&tail->alo_empty);           // lo planes may be refilled
+                            mma_bf16_keep_a(t_rc, a_hi + kk * kStepK, b_hi + kk * kStepK, idesc_rc, acc);
+                            mma_bf16_reuse_a(t_rc, a_hi + kk * kStepK, b_lo + kk * kStepK, idesc_rc, 1u);
+                        } else {
+                            mma_bf16(t_rc, a_hi + kk * kStepK, b_hi + kk * kStepK, idesc_rc, acc);
                         }
-                        mma_bf16(d_wg, wg_hi, wg_b, idesc_wg, PLANES == 2 ? 1u : acc0);
-#pragma unroll
-                        for (int ks = 1; ks < 8; ++ks) mma_bf16(d_wg, wg_hi + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, 1u);
-                        // dA always has its lo plane (it never leaves the SM, the extra pass is free on an idle tensor pipe):
-                        // in the single-plane (bf16 storage) mode only the STORED operands are rounded to bf16
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_bf16(d_wg, wg_hi + ks * kStepMN, wg_b + kTileEnc + ks * kStepMN, idesc_wg, 1u);
-                        if (c == 3 && a_sync) mma_commit(&tail->ahi_empty[i & 1]);       // this tile's hi buffer may be refilled
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks)
-                            mma_bf16(t_db + (uint32_t)c * 16, wg_b + ks * kStepMN, db_b, idesc_db, (i > 0 || ks > 0) ? 1u : 0u);
-                        mma_commit(&tail->d_empty);
                     }
-                    __syncwarp();
                 }
             }
-            if (leader) mma_commit(&tail->done);
+        };
+        // lo-plane pass (PLANES == 2): G += A_lo . W_hi; then the chunk's weight slot and the accumulator are handed over
+        auto issue_r_lo_and_commit = [&]() {
+            if (PLANES == 2) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if (s < nseg) {
+                        const uint64_t a_lo = rc_a + (uint64_t)(4 + s) * kTileEnc;
+                        const uint64_t b_hi = rc_b + (uint64_t)(s * 2) * kChunkEnc;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) mma_bf16(t_rc, a_lo + kk * kStepK, b_hi + kk * kStepK, idesc_rc, 1u);
+                    }
+                }
+            }
+            mma_commit(&tail->w_empty[0]);
+            mma_commit(&tail->r_full);
+        };
+
+        if (nseg > 0 && my_tiles > 0) {              // R_0
+            mbar_wait_p(&tail->ahi_full[0], 0, 3);
+            mbar_wait_p(&tail->w_full[0], 0, 0);
+            if (PLANES == 2) mbar_wait_p(&tail->alo_full, 0, 3);
+            tc_fence_after();
+            if (leader) {
+                issue_r_hi(0);
+                issue_r_lo_and_commit();
+            }
             __syncwarp();
-            TC_PROF_FLUSH(6, leader)
-        } else {
-            // ---- D: [dx_below | dh_prev] += dA_c . Wp[:, chunk c]^T   (N = 64 * nseg, K = 64) ----
-            const uint64_t dg_a = desc16_k(da_u);                              // dA hi; lo: + kTileEnc
-            const uint64_t dg_b = desc16_mn(w_u, 2 * kBWChunkTile);            // + stage * kStageEnc (+ kChunkEnc: lo plane)
-            const uint32_t t_dg = tmem_base + kDgCol;
-            uint32_t dcount = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                for (int c = 0; c < 4; ++c, ++dcount) {
-                    if (nseg > 0) mbar_wait_p(&tail->w_full[1], dcount & 1, 0);
-                    mbar_wait_p(&tail->d_full, dcount & 1, 1);
-                    if (c == 0 && nseg > 0 && i > 0) mbar_wait_p(&tail->g_empty, (uint32_t)(i - 1) & 1, 2);
-                    tc_fence_after();
-                    if (leader) {
-                        if (nseg > 0) {
-                            const uint64_t bs = dg_b + kStageEnc;          // buffer 1: the data gradient's copy of the chunk
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                mma_bf16(t_dg, dg_a + kk * kStepK, bs + kk * kStepMN, idesc_dg, (c > 0 || kk > 0) ? 1u : 0u);
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)                       // dA lo plane: always (see the W warp)
-                                mma_bf16(t_dg, dg_a + kTileEnc + kk * kStepK, bs + kk * kStepMN, idesc_dg, 1u);
-                            if (PLANES == 2) {
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    mma_bf16(t_dg, dg_a + kk * kStepK, bs + kChunkEnc + kk * kStepMN, idesc_dg, 1u);
-                            }
-                            mma_commit(&tail->w_empty[1]);
-                        }
-                        mma_commit(&tail->d_empty);
-                        if (c == 3 && nseg > 0) mma_commit(&tail->g_full);
-                    }
-                    __syncwarp();
-                }
-            }
-            TC_PROF_FLUSH(7, leader)
         }
+        for (uint32_t g = 0; g < total; ++g) {
+            const int i = (int)(g >> 2), c = (int)(g & 3);
+            const bool have_next = nseg > 0 && g + 1 < total;
+            // ---- (1) recompute of the next chunk ----
+            if (have_next) {
+                const uint32_t wc = g + 1;
+                mbar_wait_p(&tail->w_full[0], wc & 1, 0);
+                if (c == 3) mbar_wait_p(&tail->ahi_full[(i + 1) & 1], (uint32_t)((i + 1) >> 1) & 1, 3);
+                mbar_wait_p(&tail->r_empty, (wc & 1) ^ 1, 2);
+                tc_fence_after();
+                if (leader) {
+                    issue_r_hi(wc);
+                    if (c != 3) issue_r_lo_and_commit();         // (c == 3: the next tile's lo planes land after W_g's lo pass)
+                }
+                __syncwarp();
+            }
+            // ---- (2) dA_g is in shared memory: weight gradient, data gradient, bias gradient ----
+            if (nseg > 0) mbar_wait_p(&tail->w_full[1], g & 1, 0);
+            mbar_wait_p(&tail->d_full, g & 1, 1);
+            if (c == 0 && nseg > 0 && i > 0) mbar_wait_p(&tail->g_empty, (uint32_t)(i - 1) & 1, 2);
+            tc_fence_after();
+            if (leader) {
+                const uint64_t wg_hi = wg_hi0 + (uint64_t)((i & 1) * 2) * kTileEnc;
+                const uint32_t d_wg = t_wg + (uint32_t)c * 64;
+                const uint32_t acc0 = (i > 0) ? 1u : 0u;
+                if (PLANES == 2) {                   // W_g, lo-plane pass first: the tile's last one releases the single lo buffer a.s.a.p.
+                    mma_bf16(d_wg, wg_lo, wg_b, idesc_wg, acc0);
+#pragma unroll
+                    for (int ks = 1; ks < 8; ++ks) mma_bf16(d_wg, wg_lo + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, 1u);
+                    if (c == 3 && a_sync) mma_commit(&tail->alo_empty);
+                }
+                if (nseg > 0) {                      // D_g: [dx_below | dh_prev] += (dA_hi + dA_lo) . W_hi^T + dA_hi . W_lo^T
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
+                        if (PLANES == 2) {
+                            mma_bf16_keep_a(t_dg, dg_a + kk * kStepK, dg_b + kk * kStepMN, idesc_dg, acc);
+                            mma_bf16_reuse_a(t_dg, dg_a + kk * kStepK, dg_b + kChunkEnc + kk * kStepMN, idesc_dg, 1u);
+                        } else {
+                            mma_bf16(t_dg, dg_a + kk * kStepK, dg_b + kk * kStepMN, idesc_dg, acc);
+                        }
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)                       // dA lo plane: always (it never leaves the SM)
+                        mma_bf16(t_dg, dg_a + kTileEnc + kk * kStepK, dg_b + kk * kStepMN, idesc_dg, 1u);
+                    mma_commit(&tail->w_empty[1]);
+                    if (c == 3) mma_commit(&tail->g_full);
+                }
+                // W_g, hi planes: A_hi^T . (dA_hi + dA_lo); dA always has its lo plane: in the single-plane (bf16 storage) mode
+                // only the STORED operands are rounded to bf16
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    mma_bf16_keep_a(d_wg, wg_hi + ks * kStepMN, wg_b + ks * kStepMN, idesc_wg, (PLANES == 2 || ks > 0) ? 1u : acc0);
+                    mma_bf16_reuse_a(d_wg, wg_hi + ks * kStepMN, wg_b + kTileEnc + ks * kStepMN, idesc_wg, 1u);
+                }
+                if (c == 3 && a_sync) mma_commit(&tail->ahi_empty[i & 1]);       // this tile's hi buffer may be refilled
+                // bias gradient on the tensor pipe: D[128 x 16] += dA_c^T (MN-major A, M = 64 columns of the hi plane | 64 of the
+                // lo plane: the two planes are the two 64-element atoms, LBO = one tile) . ones[K = 16 rows][16].  Lane m < 64 of
+                // the accumulator holds sum_rows hi(dA)[:, m], lane 64 + m the lo plane's sum; all 16 columns are equal.
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    mma_bf16(t_db + (uint32_t)c * 16, wg_b + ks * kStepMN, db_b, idesc_db, (i > 0 || ks > 0) ? 1u : 0u);
+                mma_commit(&tail->d_empty);
+            }
+            __syncwarp();
+            // ---- (3) tile boundary: the next tile's lo planes were requested when W_g's lo pass released the buffer ----
+            if (have_next && c == 3) {
+                if (PLANES == 2) {
+                    mbar_wait_p(&tail->alo_full, (uint32_t)(i + 1) & 1, 3);
+                    tc_fence_after();
+                }
+                if (leader) issue_r_lo_and_commit();
+                __syncwarp();
+            }
+        }
+        if (leader && my_tiles > 0) mma_commit(&tail->done);
+        __syncwarp();
+        TC_PROF_FLUSH(4, leader)
     } else {
         // ===================== compute warps =====================
         TC_PROF_DECL
@@ -866,7 +867,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(&tail->g_empty);
         };
-        Raw cur, nxt;
+        Raw cur, nxt;              // (measured and rejected: loading two chunks ahead -- the 16 extra registers at the 96-register
+                                   //  cap cost more than the covered latency gained: 8.43 -> 8.68 ms per branch)
         const int gstep = (int)gridDim.x;
         int tile = (int)blockIdx.x;
         load_raw(tile, 0, nxt);

@@ -61,6 +61,32 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
         : "memory");
 }
 
+// Two consecutive MMAs of ONE issuing thread that share their A operand: the first keeps A in the tensor core's collector
+// buffer (SASS: A_KEEP), the second takes it from there (A_REUSE) instead of reading the 4 KB from shared memory again.
+// In the 3xBF16 scheme the pairs (A_hi . B_hi, A_hi . B_lo) share A: one of three A reads disappears -- these kernels are
+// bound by the shared-memory data pipe the operand reads go through (ncu: l1tex data pipe 94 % in the backward).
+// Only valid when no other thread issues MMAs in between (single MMA-issuing thread per CTA).
+__device__ __forceinline__ void mma_bf16_keep_a(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_bf16_reuse_a(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // ---- bf16 hi / lo split ------------------------------------------------------------------------------------
 // two fp32 -> packed bf16x2 (round to nearest even); low half = a, high half = b
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {

@@ -5,7 +5,7 @@
 
 Prints, per role, the share of the role's lifetime spent blocked on each barrier class.
 forward : producer (0: stage empty) | MMA (1: stage full, 2: TMEM empty) | epilogue (3: TMEM full)
-backward: compute (0: dA buffer free, 1: recompute ready, 2: data-gradient accumulator ready, 3: A planes free [layer 0])
+backward: compute (0: dA buffer free, 1: recompute ready, 2: data-gradient accumulator ready, 3: recompute of a tile's first chunk ready)
           MMA (0: weight chunk landed, 1: dA ready, 2: recompute buffer / dgrad accumulator free, 3: A planes landed)
           producer (0: weight stage free, 1: A planes free)
 """
@@ -18,7 +18,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "st-mgcn_b200"))
 from stmgcn_b200 import _lib, ops  # noqa: E402
 
-ROLES = {0: "fwd producer", 1: "fwd mma", 2: "fwd epilogue", 3: "bwd compute", 4: "bwd mma R", 6: "bwd mma W", 7: "bwd mma D", 5: "bwd producer"}
+ROLES = {0: "fwd producer", 1: "fwd mma", 2: "fwd epilogue", 3: "bwd compute", 4: "bwd mma", 5: "bwd producer"}
 
 
 def read(reset=True):
