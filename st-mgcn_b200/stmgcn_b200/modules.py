@@ -182,9 +182,11 @@ class ST_MGCN(nn.Module):
             assert self.sta_K == sta_adj_list[m].shape[0]
             ssets.append(supports_from_dense(sta_adj_list[m]))
         feats = []
-        if self.M > 1 and _graph_streams_enabled() and not torch.cuda.is_current_stream_capturing():
+        if self.M > 1 and _graph_streams_enabled():
             # the M graph branches are independent until the fusion: one CUDA stream per branch keeps the device's work
             # queue full across kernel boundaries (autograd replays each branch's backward on the same stream)
+            # (also under CUDA-graph capture: the fork / join below is the capturable event pattern, so the captured graph
+            # keeps the three branches as parallel chains)
             main = torch.cuda.current_stream()
             start = main.record_event()
             streams = self._branch_streams(obs_seq.device)
