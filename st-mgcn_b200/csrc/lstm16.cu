@@ -6,7 +6,7 @@
 //        arithmetic; P = 1: hi only, the bf16 mode).  A 128-row x 64-column piece of a plane IS a K-major, 128-byte
 //        swizzled tcgen05 operand tile once a TMA tensor load has put it into shared memory -- no splitter warps, no
 //        per-thread loads, no proxy fences on the operand path.
-//   cs : (L, T, rows_pad, 64) fp32, tile-blocked ([tile][unit/4][128 rows][4 units], see ws_off): the 32 lanes of a warp
+//   cs : (L, T, rows_pad, 64) fp32, tile-blocked ([tile][unit/4][128 rows][4 units], see below): the 32 lanes of a warp
 //        (32 consecutive rows, the same 4 units) touch ONE contiguous 512-byte run per access.  (With 8-unit groups every
 //        access was 16 bytes at a 32-byte stride: 32 half-used sectors and ~22 L1 data-pipe wavefronts per request; ncu
 //        showed the L1 data pipe -- tensor-core operand reads + LSU -- at 77 % (forward) / 90 % (backward) of its peak.)
@@ -42,10 +42,8 @@ constexpr int kMaxC = 4;
 constexpr int kWTileBytes = kGateCols * 128;          // [256 gate cols][64 k] bf16 = 32 KB
 constexpr int kATileBytes = kTile16Bytes;             // [128 rows][64 k] bf16 = 16 KB
 
-// element (row r, unit u) of a tile-blocked (rows_pad x 64) fp32 workspace
-__device__ __forceinline__ int64_t ws_off(int64_t r, int unit) {
-    return (((r >> 7) * 16 + (unit >> 2)) * kTileM + (r & 127)) * 4 + (unit & 3);
-}
+// element (row r, unit u) of a tile-blocked (rows_pad x 64) fp32 workspace lives at
+//   (((r >> 7) * 16 + (unit >> 2)) * 128 + (r & 127)) * 4 + (unit & 3)        (host side: ops.to_blocked / from_blocked)
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -513,7 +511,6 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     const int lane = tid & 31;
     constexpr int kMmaWarp = kBCompWarps;
     constexpr int kProdWarp = kBCompWarps + 1;
-    constexpr int kCompThreads = kBCompWarps * 32;
     // TMEM columns: weight grad (256) | data grad (128) | recompute (64, single buffer: the compute warps hold it only for
     // the TMEM -> register copy at the start of a chunk) | bias grad (4 chunks x 16)
     constexpr uint32_t kWgCol = 0, kDgCol = 256, kRcCol = 384, kDbCol = 448;
