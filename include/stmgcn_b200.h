@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define STMGCN_ABI_VERSION 2
+#define STMGCN_ABI_VERSION 3
 
 /* error codes < 0 */
 #define STMGCN_ERR_ARG      (-1)   /* null pointer / bad enum */
@@ -181,18 +181,23 @@ int32_t stmgcn_lstm16_step_fwd(int32_t t, int32_t t_len, int32_t n_layers, int64
 
 /* grid (CTAs) the lstm16 kernels use for `rows` rows: the number of weight-gradient scratch slices per layer */
 int32_t stmgcn_lstm16_grid(int64_t rows);
-/* BPTT step t (call t = T-1 .. 0), all layers top-down: recomputes the gates from hp, forms dA, accumulates the weight
- * gradients and propagates [dx_below | dh_prev] -- one fused kernel per layer.  Workspaces (tile-blocked, R_pad rows):
- * d_top (R_pad,64): gradient of the top layer's last hidden state; dh_rec, dc: (L,R_pad,64); dx_work: (R_pad,64); none needs
- * initialisation.  Accumulates (+=; caller zeroes): d_s (B,T), dbp[l] (256, gate-interleaved).  dw_scratch:
- * (L, stmgcn_lstm16_grid(rows), 128*256) floats, no initialisation needed (the call with t = T-1 writes it). */
-int32_t stmgcn_lstm16_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t c_in,
-                               int64_t b_inner, int32_t planes, const float* xo, const float* s_gate,
-                               const void* const* wimg, const float* const* bias, const float* wih_t,
-                               const void* h0p, const float* c0, const void* hp, const float* cs,
-                               const float* d_top, float* dh_rec, float* dc, float* dx_work, float* d_s,
-                               float* const* dbp, float* dw_scratch, void* stream);
-/* After all stmgcn_lstm16_step_bwd calls: sum layer `layer`'s scratch slices into nn.LSTM-native gradients
+/* BPTT of ONE layer through all timesteps T-1 .. 0 in one launch (call the layers top-down): recomputes the gates from
+ * hp, forms dA, accumulates the weight and bias gradients and propagates [dx_below | dh_prev].  A tile's rows never mix with
+ * other tiles', so each CTA walks its own tiles through time; only the layer order synchronises.  T <= 64.
+ * Workspaces (tile-blocked, R_pad = ceil(R/128)*128 rows; none needs initialisation):
+ *   dh_in : top layer: d_top (R_pad,64), the gradient of the top layer's last hidden state; other layers: the dx_out
+ *           (T,R_pad,64) the layer above wrote;      dx_out: (T,R_pad,64), NULL for layer 0;
+ *   dh_rec, dc: (R_pad,64) scratch of this layer;    dw_scratch: (stmgcn_lstm16_grid(rows), 128*256) floats;
+ *   zero_tile: 16 KB of zeros (the h_prev operand at t = 0 without an initial state).
+ * wimg / bias: this layer's operands from stmgcn_lstm16_pack.  Accumulates (+=; caller zeroes): d_s (B,T), dbp (256,
+ * gate-interleaved). */
+int32_t stmgcn_lstm16_layer_bwd(int32_t layer, int32_t t_len, int32_t n_layers, int64_t rows, int32_t c_in,
+                                int64_t b_inner, int32_t planes, const float* xo, const float* s_gate,
+                                const void* wimg, const float* bias, const float* wih_t, const void* h0p,
+                                const float* c0, const void* hp, const float* cs, const float* dh_in,
+                                float* dx_out, float* dh_rec, float* dc, float* d_s, float* dbp,
+                                float* dw_scratch, const void* zero_tile, void* stream);
+/* After stmgcn_lstm16_layer_bwd of layer `layer`: sum its scratch slices into nn.LSTM-native gradients
  * d_w_ih (256, in), d_w_hh (256, 64), d_b_ih = d_b_hh (256) (overwritten, not accumulated). */
 int32_t stmgcn_lstm16_wgrad_reduce(int32_t layer, int32_t c_in, int32_t n_slices, const float* slices,
                                    const float* dbp, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh,

@@ -462,33 +462,42 @@ constexpr int kBATiles = 6;                             // hi planes of two tile
 constexpr size_t kBSmem = 1024 + kBATiles * (size_t)kATileBytes + (size_t)kBWStages * kBWStageBytes + 2 * (size_t)kATileBytes + sizeof(B16Tail);
 static_assert(kBSmem <= 232448, "lstm16 backward kernel exceeds the 227 KB shared-memory limit");
 
+// One launch = one LAYER, all timesteps T-1 .. 0 (the tiles of a CTA are its own through time: rows never mix).  A step
+// of a tile needs what the SAME CTA produced for that tile one step later (dh_rec, dc: global, in place), so nothing but
+// the launch order of the layers (top down) synchronises; what a per-step launch paid 36 times per branch -- prologue,
+// first-tile latency, the 128 KB weight-gradient flush per CTA, the launch gap: 22 us of a 169 us launch, measured by
+// scaling the row count -- is paid 3 times.
+constexpr int kBMaxSteps = 64;
+struct Bwd16Step {
+    int32_t slice[2];          // plane slice of K segment s in its tensor map (hi plane; lo = + 1)
+    int8_t src[2];             // 0: maps[0] (hp), 1: maps[1] (h0p), 2: zeros (h_prev at t = 0 without an initial state)
+    int8_t first;              // t == T-1: incoming dh_rec / dc are zero and not read
+    int8_t store_dh;           // write dh_prev (t > 0 or an initial state exists)
+    int32_t t;
+    const float* c_prev;       // blocked or nullptr (zeros)
+    const float* dh_in;        // blocked or nullptr: gradient from the layer above at this step (top layer: d_top at T-1)
+    float* dx_out;             // blocked or nullptr (layer 0)
+};
 struct Bwd16Params {
-    alignas(64) CUtensorMap amap[2];
-    int aslice[2];
-    int nseg;                  // K segments of the gate GEMM present (0, 1, 2)
-    int layer0;                // 1: layer 0 (segment = h_prev only; tiles 2,3 of the A region hold the [x*s] auxiliary operand)
+    alignas(64) CUtensorMap maps[2];
+    const uint8_t* zero_tile;  // 16 KB of zeros
     const uint8_t* wimg;
     const float* bias;
     const float* wih;          // layer 0: (C,256) gate-interleaved
     const float* xo;           // (rows, T, C)
     const float* sg;           // (B, T)
     float* d_s;                // (B, T) +=   (layer 0)
-    int c_in, t, t_len;
+    int c_in, t_len, n_steps;
     int64_t b_inner;
-    const float* c_prev;       // blocked or nullptr
-    const float* dh_in;        // blocked or nullptr: gradient from the layer above (or d_top)
-    float* dh_rec;             // blocked, in (unless first) / out
-    float* dc;                 // blocked, in (unless first) / out
-    float* dx_out;             // blocked or nullptr (layer 0)
-    int first;                 // t == T-1: incoming dh_rec / dc are zero and not read
-    int store_dh;              // write dh_prev (t > 0 or an initial state exists)
+    float* dh_rec;             // blocked, in (unless first) / out, in place through the steps
+    float* dc;                 // blocked, in (unless first) / out, in place through the steps
     float* dbp;                // (256) +=  gate-interleaved bias gradient
-    float* dw_slice;           // this launch's scratch: gridDim.x slices of 128*256 floats (accumulator register layout)
-    int dw_first;              // 1: first launch of this layer: slices are written, not accumulated
-    int flush_lo, flush_hi;    // accumulator rows [0,64) / [64,128) carry a valid gradient in this launch
+    float* dw_slice;           // gridDim.x slices of 128*256 floats (accumulator register layout), written once
     int64_t rows;
     int n_tiles;
+    Bwd16Step steps[kBMaxSteps];   // in execution order: steps[0] is t = T-1
 };
+static_assert(sizeof(Bwd16Params) <= 4096, "kernel parameter block exceeds 4 KB");
 
 template <int PLANES, int CIN>                                  // CIN: see lstm16_fwd_kernel
 __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_constant__ Bwd16Params p) {
@@ -549,53 +558,66 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     const uint32_t tmem_base = tail->tmem_base;
     const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const bool have_aux = L0;
+    // K segments of the gate GEMM: layers > 0: [h_below | h_prev]; layer 0: [h_prev] (at t = 0 without an initial state the
+    // h_prev tiles are loaded as zeros: every step of a layer has the same operand geometry and accumulates into the same
+    // weight-gradient rows)
+    constexpr int kNseg = L0 ? 1 : 2;
+    const int n_items = my_tiles * p.n_steps;                      // work items (step, tile), step-major
     // operand tiles of the weight-gradient GEMM (MN-major view): atom 0 and atom 1 along M = kd
-    // layers > 0: atom 0 = h_below, atom 1 = h_prev (absent: duplicate of atom 0, rows 64.. are not flushed)
-    // layer 0   : atom 0 = h_prev (absent at t = 0: duplicate of the auxiliary tile), atom 1 = auxiliary [x*s] tile
-    const uint32_t wg_a0 = (L0 && p.nseg == 0) ? 1u : 0u;          // segment slot of atom 0
-    const uint32_t wg_lbo = (L0 ? (p.nseg == 0 ? 0u : 1u) : (p.nseg == 2 ? 1u : 0u)) * kATileBytes;
+    // layers > 0: atom 0 = h_below, atom 1 = h_prev;  layer 0: atom 0 = h_prev, atom 1 = auxiliary [x*s] tile
+    constexpr uint32_t wg_a0 = 0u;                                 // segment slot of atom 0
+    constexpr uint32_t wg_lbo = kATileBytes;
 
     if (warp == kProdWarp) {
         // ===================== producer =====================
         TC_PROF_DECL
         const bool leader = elect_one_sync();
-        if (leader && p.nseg > 0 && my_tiles > 0) {
+        if (leader && n_items > 0) {
             const int first = (int)blockIdx.x, gstep = (int)gridDim.x;
-            auto load_hi = [&](int i) {                 // hi planes of tile i -> hi buffer i & 1
-                const int b = i & 1;
-                if (i >= 2) mbar_wait_p(&tail->ahi_empty[b], (uint32_t)((i >> 1) - 1) & 1, 1);
-                mbar_arrive_expect_tx(&tail->ahi_full[b], (uint32_t)(p.nseg * kATileBytes));
-                for (int s = 0; s < p.nseg; ++s)
-                    tma_load_3d(a_sm + (size_t)(b * 2 + s) * kATileBytes, &p.amap[s], 0, (first + i * gstep) * kTileM, p.aslice[s],
-                                &tail->ahi_full[b]);
+            // work item w = (step w / my_tiles, tile first + (w % my_tiles) * gstep)
+            auto seg_load = [&](uint8_t* dst, const Bwd16Step& sp, int sg, int plane, int tile, uint64_t* bar) {
+                if (sp.src[sg] == 2) bulk_g2s(dst, p.zero_tile, kATileBytes, bar);
+                else tma_load_3d(dst, &p.maps[sp.src[sg]], 0, tile * kTileM, sp.slice[sg] + plane, bar);
             };
-            auto load_lo = [&](int i) {                 // lo planes of tile i -> the single lo buffer
-                if (i >= 1) mbar_wait_p(&tail->alo_empty, (uint32_t)(i - 1) & 1, 1);
-                mbar_arrive_expect_tx(&tail->alo_full, (uint32_t)(p.nseg * kATileBytes));
-                for (int s = 0; s < p.nseg; ++s)
-                    tma_load_3d(a_sm + (size_t)(4 + s) * kATileBytes, &p.amap[s], 0, (first + i * gstep) * kTileM, p.aslice[s] + 1,
-                                &tail->alo_full);
+            auto load_hi = [&](int w) {                 // hi planes of item w -> hi buffer w & 1
+                const int b = w & 1;
+                const int st = w / my_tiles, tile = first + (w - st * my_tiles) * gstep;
+                const Bwd16Step& sp = p.steps[st];
+                if (w >= 2) mbar_wait_p(&tail->ahi_empty[b], (uint32_t)((w >> 1) - 1) & 1, 1);
+                mbar_arrive_expect_tx(&tail->ahi_full[b], (uint32_t)(kNseg * kATileBytes));
+                for (int sg = 0; sg < kNseg; ++sg)
+                    seg_load(a_sm + (size_t)(b * 2 + sg) * kATileBytes, sp, sg, 0, tile, &tail->ahi_full[b]);
+            };
+            auto load_lo = [&](int w) {                 // lo planes of item w -> the single lo buffer
+                const int st = w / my_tiles, tile = first + (w - st * my_tiles) * gstep;
+                const Bwd16Step& sp = p.steps[st];
+                if (w >= 1) mbar_wait_p(&tail->alo_empty, (uint32_t)(w - 1) & 1, 1);
+                mbar_arrive_expect_tx(&tail->alo_full, (uint32_t)(kNseg * kATileBytes));
+                for (int sg = 0; sg < kNseg; ++sg)
+                    seg_load(a_sm + (size_t)(4 + sg) * kATileBytes, sp, sg, 1, tile, &tail->alo_full);
             };
             auto load_w = [&](int stg, uint32_t wc) {   // weight chunk wc & 3 -> buffer stg (0: the recompute's copy, 1: the
                 const int c = wc & 3;                   // data gradient's copy); use wc of a buffer waits for release wc - 1
                 mbar_wait_p(&tail->w_empty[stg], (wc & 1) ^ 1, 0);
-                mbar_arrive_expect_tx(&tail->w_full[stg], (uint32_t)(p.nseg * PLANES * kBWChunkTile));
-                for (int s = 0; s < p.nseg; ++s)
+                mbar_arrive_expect_tx(&tail->w_full[stg], (uint32_t)(kNseg * PLANES * kBWChunkTile));
+                for (int sg = 0; sg < kNseg; ++sg)
                     for (int pl = 0; pl < PLANES; ++pl)
-                        bulk_g2s(w_sm + (size_t)stg * kBWStageBytes + (size_t)(s * 2 + pl) * kBWChunkTile,
-                                 p.wimg + (size_t)(s * 2 + pl) * kWTileBytes + (size_t)c * kBWChunkTile, kBWChunkTile, &tail->w_full[stg]);
+                        bulk_g2s(w_sm + (size_t)stg * kBWStageBytes + (size_t)(sg * 2 + pl) * kBWChunkTile,
+                                 p.wimg + (size_t)(sg * 2 + pl) * kWTileBytes + (size_t)c * kBWChunkTile, kBWChunkTile, &tail->w_full[stg]);
             };
-            auto prefetch_next = [&](int i) {           // tile i's lo planes and per-row inputs -> L2
-                const int tile = first + i * gstep;
+            auto prefetch_next = [&](int w) {           // item w's lo planes and per-row inputs -> L2
+                const int st = w / my_tiles, tile = first + (w - st * my_tiles) * gstep;
+                const Bwd16Step& sp = p.steps[st];
                 if (PLANES == 2)
-                    for (int s = 0; s < p.nseg; ++s) tma_prefetch_3d(&p.amap[s], 0, tile * kTileM, p.aslice[s] + 1);
+                    for (int sg = 0; sg < kNseg; ++sg)
+                        if (sp.src[sg] != 2) tma_prefetch_3d(&p.maps[sp.src[sg]], 0, tile * kTileM, sp.slice[sg] + 1);
                 // the compute warps' per-row inputs (a tile is one contiguous 32 KB run in every workspace): their
                 // one-chunk-ahead register prefetch then costs an L2 hit, not a DRAM round trip
                 const int64_t o = (int64_t)tile * kTileM * kHid;
                 constexpr uint32_t kB = kTileM * kHid * 4;
-                if (p.c_prev) prefetch_l2(p.c_prev + o, kB);
-                if (p.dh_in) prefetch_l2(p.dh_in + o, kB);
-                if (!p.first) {
+                if (sp.c_prev) prefetch_l2(sp.c_prev + o, kB);
+                if (sp.dh_in) prefetch_l2(sp.dh_in + o, kB);
+                if (!sp.first && my_tiles > 2) {         // (written by this CTA more than a tile-time ago)
                     prefetch_l2(p.dh_rec + o, kB);
                     prefetch_l2(p.dc + o, kB);
                 }
@@ -612,8 +634,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             load_w(0, 0);
             load_w(1, 0);
             load_w(0, 1);
-            for (int i = 0; i < my_tiles; ++i) {
-                const bool more = i + 1 < my_tiles;
+            for (int i = 0; i < n_items; ++i) {
+                const bool more = i + 1 < n_items;
                 const uint32_t g0 = 4u * (uint32_t)i;
                 if (more) {
                     load_hi(i + 1);
@@ -650,12 +672,12 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         constexpr uint32_t idesc_rc = idesc_bf16(kTileM, 64);              // recompute: A K-major, B K-major, N = 64
         constexpr uint32_t idesc_wg = idesc_bf16(kTileM, 64, 1, 1);        // weight gradient: both MN-major, M = kd (128), N = 64
         constexpr uint32_t idesc_db = idesc_bf16(kTileM, 16, 1, 0);        // bias gradient: A = dA^T (hi | lo atoms), B = ones
-        const uint32_t idesc_dg = idesc_bf16(kTileM, 64 * (p.nseg > 0 ? p.nseg : 1), 0, 1);   // data gradient: B MN-major, N = 64 * nseg
+        constexpr uint32_t idesc_dg = idesc_bf16(kTileM, 64 * kNseg, 0, 1);   // data gradient: B MN-major, N = 64 * nseg
         const uint32_t a_u = smem_u32(a_sm), w_u = smem_u32(w_sm), da_u = smem_u32(da_sm);
         constexpr uint64_t kStepK = 2;                                     // K-major: 16 bf16 = 32 bytes
         constexpr uint64_t kStepMN = 2048 >> 4;                            // MN-major: 16 rows of 128 bytes
         constexpr uint64_t kTileEnc = kATileBytes >> 4, kChunkEnc = kBWChunkTile >> 4, kStageEnc = kBWStageBytes >> 4;
-        const int nseg = p.nseg;
+        constexpr int nseg = kNseg;
         const uint64_t rc_a = desc16_k(a_u);                               // hi: + (buffer*2 + s) * kTileEnc; lo: + (4 + s) * kTileEnc
         const uint64_t rc_b = desc16_k(w_u);                               // buffer 0 (the recompute's copy): + (s*2 + plane) * kChunkEnc
         const uint64_t wg_hi0 = desc16_mn(a_u + wg_a0 * kATileBytes, wg_lbo);              // hi buffer 0; buffer 1: + 2 * kTileEnc
@@ -666,7 +688,8 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         const uint64_t dg_b = desc16_mn(w_u, 2 * kBWChunkTile) + kStageEnc;   // buffer 1 (the data gradient's copy) (+ kChunkEnc: lo plane)
         const uint32_t t_rc = tmem_base + kRcCol, t_wg = tmem_base + kWgCol, t_db = tmem_base + kDbCol, t_dg = tmem_base + kDgCol;
         const bool a_sync = nseg > 0 || L0;          // someone waits for the A buffers (producer and / or the aux-tile writers)
-        const uint32_t total = 4u * (uint32_t)my_tiles;
+        const uint32_t total = 4u * (uint32_t)n_items;    // chunks; "tile" below = work item (step, tile): the hand-offs do
+                                                          // not care which timestep an item belongs to
 
         // hi-plane passes of the recompute of chunk wc (tile wc >> 2): G = A_hi . (W_hi + W_lo)
         auto issue_r_hi = [&](uint32_t wc) {
@@ -706,7 +729,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             mma_commit(&tail->r_full);
         };
 
-        if (nseg > 0 && my_tiles > 0) {              // R_0
+        if (n_items > 0) {                           // R_0
             mbar_wait_p(&tail->ahi_full[0], 0, 3);
             mbar_wait_p(&tail->w_full[0], 0, 0);
             if (PLANES == 2) mbar_wait_p(&tail->alo_full, 0, 3);
@@ -792,7 +815,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 __syncwarp();
             }
         }
-        if (leader && my_tiles > 0) mma_commit(&tail->done);
+        if (leader && n_items > 0) mma_commit(&tail->done);
         __syncwarp();
         TC_PROF_FLUSH(4, leader)
     } else {
@@ -815,35 +838,41 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         // of d_s is summed in a register and added once (one shared-memory float atomic = a CAS loop; 16 per address and tile
         // were 6 % of the layer-0 kernel's stall samples)
         const bool ds_fixed = L0 && (kTileM % (uint32_t)p.b_inner) == 0u;
+        const bool ds_smem = L0 && (int64_t)p.n_steps * p.b_inner <= kBSgMax;    // s_ds holds [step][window]
         float ds_acc = 0.f;
-        auto load_x = [&](int tile_n) {
+        // (st, tile): step index and tile of a work item; a step index >= n_steps marks "no such item"
+        auto load_x = [&](int st, int tile_n) {
             const uint32_t rn = (uint32_t)tile_n * kTileM + row_in_tile;
-            const bool ok = tile_n < p.n_tiles && rn < rows32;
+            const bool ok = st < p.n_steps && rn < rows32;
+            const uint32_t t = ok ? (uint32_t)p.steps[st].t : 0u;
             sv_next = 0.f;
-            if (ok) sv_next = p.sg[(rn % (uint32_t)p.b_inner) * (uint32_t)p.t_len + (uint32_t)p.t];      // (32-bit: a 64-bit % is a call)
+            if (ok) sv_next = p.sg[(rn % (uint32_t)p.b_inner) * (uint32_t)p.t_len + t];      // (32-bit: a 64-bit % is a call)
 #pragma unroll
             for (int c = 0; c < kMaxC; ++c)
-                xraw_next[c] = (c < kC && ok && (CIN == 1 || c < p.c_in)) ? p.xo[((int64_t)rn * p.t_len + p.t) * p.c_in + c] : 0.f;
+                xraw_next[c] = (c < kC && ok && (CIN == 1 || c < p.c_in)) ? p.xo[((int64_t)rn * p.t_len + t) * p.c_in + c] : 0.f;
         };
-        auto load_raw = [&](int tile, int c, Raw& rw) {
+        auto load_raw = [&](int st, int tile, int c, Raw& rw) {
             const uint32_t r = (uint32_t)tile * kTileM + row_in_tile;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             rw.cp = rw.dhi = rw.dhr = rw.dcv = z;
-            if (tile < p.n_tiles && r < rows32) {
+            if (st < p.n_steps && r < rows32) {
+                const Bwd16Step& sp = p.steps[st];
                 const uint32_t o = (uint32_t)tile * 8192u + (uint32_t)c * 2048u + thr_off;
-                if (p.c_prev) rw.cp = *reinterpret_cast<const float4*>(p.c_prev + o);
-                if (p.dh_in) rw.dhi = *reinterpret_cast<const float4*>(p.dh_in + o);
-                if (!p.first) {
+                if (sp.c_prev) rw.cp = *reinterpret_cast<const float4*>(sp.c_prev + o);
+                if (sp.dh_in) rw.dhi = *reinterpret_cast<const float4*>(sp.dh_in + o);
+                if (!sp.first) {
                     rw.dhr = *reinterpret_cast<const float4*>(p.dh_rec + o);
                     rw.dcv = *reinterpret_cast<const float4*>(p.dc + o);
                 }
             }
         };
-        auto drain = [&](int i_prev, int tile_prev) {   // [dx_below | dh_prev] of tile i_prev: TMEM -> tile-blocked workspaces
+        // [dx_below | dh_prev] of work item w_prev (step st_prev, tile tile_prev): TMEM -> tile-blocked workspaces
+        auto drain = [&](int w_prev, int st_prev, int tile_prev) {
             const uint32_t r = (uint32_t)tile_prev * kTileM + row_in_tile;
-            mbar_wait(&tail->g_full, (uint32_t)i_prev & 1, 2);
+            const Bwd16Step& sp = p.steps[st_prev];
+            mbar_wait(&tail->g_full, (uint32_t)w_prev & 1, 2);
             tc_fence_after();
-            const int ncols = 64 * p.nseg;
+            constexpr int ncols = 64 * kNseg;
             if (part * 32 < ncols) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kDgCol + (uint32_t)part * 32, v);
@@ -851,9 +880,9 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 const int col = part * 32;
                 // layers > 0: columns [0,64) = dx_below, [64,128) = dh_prev; layer 0: [0,64) = dh_prev
                 const bool is_dx = !L0 && col < 64;
-                float* base = is_dx ? p.dx_out : p.dh_rec;
+                float* base = is_dx ? sp.dx_out : p.dh_rec;
                 const int unit0 = col & 63;
-                if (r < rows32 && base != nullptr && (is_dx || p.store_dh)) {
+                if (r < rows32 && base != nullptr && (is_dx || sp.store_dh)) {
                     const uint32_t o = (uint32_t)tile_prev * 8192u + row_in_tile * 4u + (uint32_t)(unit0 >> 2) * 512u;
 #pragma unroll
                     for (int k = 0; k < 8; ++k)          // units unit0 + 4k .. +3: the warp writes one contiguous 512-byte run
@@ -867,10 +896,18 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
         Raw cur, nxt;              // (measured and rejected: loading two chunks ahead -- the 16 extra registers at the 96-register
                                    //  cap cost more than the covered latency gained: 8.43 -> 8.68 ms per branch)
         const int gstep = (int)gridDim.x;
-        int tile = (int)blockIdx.x;
-        load_raw(tile, 0, nxt);
-        if (L0) load_x(tile);
-        for (int i = 0; i < my_tiles; ++i, tile += gstep) {
+        // work items in step-major order: (st, i) = (step index, this CTA's i-th tile); (st_n, tile_n) = the item after it
+        int st = 0, i = 0, tile = (int)blockIdx.x;
+        if (n_items == 0) st = p.n_steps;
+        load_raw(st, tile, 0, nxt);
+        if (L0) load_x(st, tile);
+        for (int w = 0; w < n_items; ++w) {
+            const bool last_of_step = (i + 1 == my_tiles);
+            const int st_n = last_of_step ? st + 1 : st;
+            const int tile_n = last_of_step ? (int)blockIdx.x : tile + gstep;
+            const int st_p = (i == 0) ? st - 1 : st;                                   // the item before this one
+            const int tile_p = (i == 0) ? (int)blockIdx.x + (my_tiles - 1) * gstep : tile - gstep;
+            const Bwd16Step& sp = p.steps[st];
             const uint32_t r = (uint32_t)tile * kTileM + row_in_tile;
             const bool valid = r < rows32;
             if (L0) {
@@ -883,26 +920,33 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
             }
             // (the drain sits in the tile-boundary bubble: the first recompute of this tile cannot finish before the lo planes
             // have been reloaded; moved behind chunk 0 it cost 2.3 k cycles of real time per tile, measured)
-            if (i > 0 && p.nseg > 0) drain(i - 1, tile - gstep);
+            if (w > 0) drain(w - 1, st_p, tile_p);
+            if (i == 0 && w > 0) {
+                // step boundary: this step reads the dh_rec the CTA's own drains wrote during the previous step (other threads'
+                // stores): a barrier of the 512 compute threads orders them, and the first chunk's inputs -- not prefetched
+                // across the boundary (with one tile per CTA they did not exist yet) -- are loaded behind it
+                asm volatile("bar.sync 1, %0;" ::"n"(kBCompWarps * 32) : "memory");
+                load_raw(st, tile, 0, nxt);
+            }
             if (have_aux && part == 0) {
                 // auxiliary weight-gradient operand: the seg-1 slot of this tile's hi buffer and of the lo buffer; row = this
                 // thread's row, columns 0..C-1 = x*s (hi / lo split)
-                if (i >= 2) mbar_wait(&tail->ahi_empty[i & 1], (uint32_t)((i >> 1) - 1) & 1, 3);
+                if (w >= 2) mbar_wait(&tail->ahi_empty[w & 1], (uint32_t)((w >> 1) - 1) & 1, 3);
                 uint32_t hi[2], lo[2];
                 split_bf16x2(xs[0], xs[1], hi[0], lo[0]);
                 split_bf16x2(xs[2], xs[3], hi[1], lo[1]);
                 const uint32_t row = (uint32_t)(q * 32 + lane);
                 const uint32_t off = row * 128u + ((0u ^ (row & 7u)) << 4);
-                *reinterpret_cast<uint4*>(a_sm + (size_t)((i & 1) * 2 + 1) * kATileBytes + off) = make_uint4(hi[0], hi[1], 0u, 0u);
+                *reinterpret_cast<uint4*>(a_sm + (size_t)((w & 1) * 2 + 1) * kATileBytes + off) = make_uint4(hi[0], hi[1], 0u, 0u);
                 if (PLANES == 2) {
-                    if (i >= 1) mbar_wait(&tail->alo_empty, (uint32_t)(i - 1) & 1, 3);
+                    if (w >= 1) mbar_wait(&tail->alo_empty, (uint32_t)(w - 1) & 1, 3);
                     *reinterpret_cast<uint4*>(a_sm + (size_t)5 * kATileBytes + off) = make_uint4(lo[0], lo[1], 0u, 0u);
                 }
             }
             for (int c = 0; c < 4; ++c, ++dcount) {
                 cur = nxt;
                 uint32_t v[16];
-                if (p.nseg > 0) {
+                {
                     mbar_wait(&tail->r_full, rcount & 1, c == 0 ? 3 : 1);      // (profile builds: class 3 = first chunk of a tile)
                     tc_fence_after();
                     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kRcCol + (uint32_t)part * 16, v);
@@ -911,9 +955,6 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tail->r_empty);
                     ++rcount;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = 0u;
                 }
                 const int unit0 = 16 * c + 4 * part;
                 const float cp[4] = {cur.cp.x, cur.cp.y, cur.cp.z, cur.cp.w};
@@ -978,10 +1019,11 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                 if (lane == 0) mbar_arrive(&tail->d_full);
                 // next chunk's inputs: issued AFTER the proxy fence -- fence.proxy.async implies MEMBAR.ALL.CTA, which waits for
                 // every outstanding load of the thread, so a prefetch issued before it is simply waited for at the fence
-                if (c < 3) load_raw(tile, c + 1, nxt);
+                if (c < 3) load_raw(st, tile, c + 1, nxt);
                 else {
-                    load_raw(tile + gstep, 0, nxt);
-                    if (L0) load_x(tile + gstep);
+                    // (across a step boundary the first chunk is loaded behind the step's barrier, see above)
+                    if (!last_of_step) load_raw(st_n, tile_n, 0, nxt);
+                    if (L0) load_x(st_n, tile_n);
                 }
                 if (valid)
                     *reinterpret_cast<float4*>(p.dc + ((uint32_t)tile * 8192u + (uint32_t)c * 2048u + thr_off)) =
@@ -996,16 +1038,24 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     ds_acc += contrib;
                 } else {
                     const int64_t b = (int64_t)(r % (uint32_t)p.b_inner);
-                    if (p.b_inner <= kBSgMax) atomicAdd(&tail->s_ds[b], contrib);
-                    else atomicAdd(&p.d_s[b * p.t_len + p.t], contrib);
+                    if (ds_smem) atomicAdd(&tail->s_ds[(int64_t)st * p.b_inner + b], contrib);
+                    else atomicAdd(&p.d_s[b * p.t_len + sp.t], contrib);
                 }
             }
+            if (L0 && ds_fixed && last_of_step) {       // this thread's share of d_s[b, t] for the step that ends here
+                const int64_t b = (int64_t)(row_in_tile % (uint32_t)p.b_inner);
+                if (ds_smem) atomicAdd(&tail->s_ds[(int64_t)st * p.b_inner + b], ds_acc);
+                else atomicAdd(&p.d_s[b * p.t_len + sp.t], ds_acc);
+                ds_acc = 0.f;
+            }
+            // next work item
+            if (last_of_step) { st = st + 1; i = 0; tile = (int)blockIdx.x; }
+            else { ++i; tile += gstep; }
         }
-        if (ds_fixed && my_tiles > 0) atomicAdd(&tail->s_ds[row_in_tile % (uint32_t)p.b_inner], ds_acc);   // (b_inner <= 128 <= kBSgMax)
-        if (my_tiles > 0 && p.nseg > 0) drain(my_tiles - 1, tile - gstep);
+        if (n_items > 0) drain(n_items - 1, p.n_steps - 1, (int)blockIdx.x + (my_tiles - 1) * gstep);
         TC_PROF_FLUSH(3, tid == 0)
         // ---- weight-gradient accumulator -> this CTA's scratch slice (register layout: [part][piece][vec][row m][4]) ----
-        if (my_tiles > 0) {
+        if (n_items > 0) {
             mbar_wait_raw(&tail->done, 0);
             tc_fence_after();
             float* slice = p.dw_slice + (size_t)blockIdx.x * (kTileM * kGateCols);
@@ -1029,16 +1079,7 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     float4* dst = reinterpret_cast<float4*>(slice + ((size_t)((part * 4 + j) * 4 + e) * kTileM + m) * 4);
                     float4 acc = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
                                              __uint_as_float(v[4 * e + 3]));
-                    const bool live = (q < 2) ? (p.flush_lo != 0) : (p.flush_hi != 0);      // rows m < 64 / m >= 64
-                    if (live) {
-                        // later launches of the layer add with a fire-and-forget vector reduction (the slice is private to
-                        // this CTA: no contention); a read-modify-write here waited a DRAM round trip at the very end of
-                        // every launch, where nothing overlaps it
-                        if (!p.dw_first) red_add_f32x4(dst, acc);
-                        else *dst = acc;
-                    } else if (p.dw_first) {
-                        *dst = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    *dst = acc;                  // (one launch per layer: the slice is written once, never accumulated)
                 }
             }
         }
@@ -1047,8 +1088,11 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
-    if (L0 && p.b_inner <= kBSgMax)
-        for (int i = tid; i < (int)p.b_inner; i += kBThreads) atomicAdd(&p.d_s[(int64_t)i * p.t_len + p.t], tail->s_ds[i]);
+    if (L0 && (int64_t)p.n_steps * p.b_inner <= kBSgMax)
+        for (int e = tid; e < p.n_steps * (int)p.b_inner; e += kBThreads) {
+            const int st = e / (int)p.b_inner, b = e - st * (int)p.b_inner;
+            atomicAdd(&p.d_s[(int64_t)b * p.t_len + p.steps[st].t], tail->s_ds[e]);
+        }
 }
 
 // Sum the per-CTA weight-gradient slices of one layer and write nn.LSTM-native gradients:
@@ -1220,87 +1264,84 @@ extern "C" int32_t stmgcn_lstm16_grid(int64_t rows) {
     return (int32_t)(n_tiles < sm_count() ? n_tiles : sm_count());
 }
 
-extern "C" int32_t stmgcn_lstm16_step_bwd(int32_t t, int32_t t_len, int32_t n_layers, int64_t rows, int32_t c_in,
-                                          int64_t b_inner, int32_t planes, const float* xo, const float* s_gate,
-                                          const void* const* wimg, const float* const* bias, const float* wih_t,
-                                          const void* h0p, const float* c0, const void* hp, const float* cs,
-                                          const float* d_top, float* dh_rec, float* dc, float* dx_work, float* d_s,
-                                          float* const* dbp, float* dw_scratch, void* stream) {
-    STMGCN_REQUIRE(xo && s_gate && wimg && bias && wih_t && hp && cs && d_top && dh_rec && dc && dx_work && d_s && dbp && dw_scratch,
-                   STMGCN_ERR_ARG, "lstm16_step_bwd: null pointer");
-    STMGCN_REQUIRE(planes == 1 || planes == 2, STMGCN_ERR_ARG, "lstm16_step_bwd: planes=%d", planes);
-    STMGCN_REQUIRE(t >= 0 && t < t_len && n_layers >= 1 && n_layers <= 8 && rows > 0 && c_in >= 1 && c_in <= kMaxC && b_inner > 0,
-                   STMGCN_ERR_SHAPE, "lstm16_step_bwd: t=%d T=%d L=%d rows=%lld C=%d", t, t_len, n_layers, (long long)rows, c_in);
-    STMGCN_REQUIRE(rows <= (1LL << 25), STMGCN_ERR_SHAPE, "lstm16_step_bwd: rows=%lld too large (32-bit element offsets)", (long long)rows);
-    STMGCN_REQUIRE((h0p == nullptr) == (c0 == nullptr), STMGCN_ERR_ARG, "lstm16_step_bwd: h0p and c0 go together");
+extern "C" int32_t stmgcn_lstm16_layer_bwd(int32_t layer, int32_t t_len, int32_t n_layers, int64_t rows, int32_t c_in,
+                                           int64_t b_inner, int32_t planes, const float* xo, const float* s_gate,
+                                           const void* wimg, const float* bias, const float* wih_t, const void* h0p,
+                                           const float* c0, const void* hp, const float* cs, const float* dh_in,
+                                           float* dx_out, float* dh_rec, float* dc, float* d_s, float* dbp,
+                                           float* dw_scratch, const void* zero_tile, void* stream) {
+    STMGCN_REQUIRE(xo && s_gate && wimg && bias && hp && cs && dh_in && dh_rec && dc && d_s && dbp && dw_scratch && zero_tile,
+                   STMGCN_ERR_ARG, "lstm16_layer_bwd: null pointer");
+    STMGCN_REQUIRE(planes == 1 || planes == 2, STMGCN_ERR_ARG, "lstm16_layer_bwd: planes=%d", planes);
+    STMGCN_REQUIRE(layer >= 0 && layer < n_layers && n_layers <= 8 && t_len >= 1 && t_len <= kBMaxSteps && rows > 0 && c_in >= 1 &&
+                       c_in <= kMaxC && b_inner > 0,
+                   STMGCN_ERR_SHAPE, "lstm16_layer_bwd: layer=%d L=%d T=%d (max %d) rows=%lld C=%d", layer, n_layers, t_len,
+                   kBMaxSteps, (long long)rows, c_in);
+    STMGCN_REQUIRE(rows <= (1LL << 25), STMGCN_ERR_SHAPE, "lstm16_layer_bwd: rows=%lld too large (32-bit element offsets)", (long long)rows);
+    STMGCN_REQUIRE((h0p == nullptr) == (c0 == nullptr), STMGCN_ERR_ARG, "lstm16_layer_bwd: h0p and c0 go together");
+    STMGCN_REQUIRE((layer == 0) == (dx_out == nullptr), STMGCN_ERR_ARG, "lstm16_layer_bwd: dx_out is for layers > 0 only");
+    STMGCN_REQUIRE(layer > 0 || wih_t != nullptr, STMGCN_ERR_ARG, "lstm16_layer_bwd: wih_t null");
     cudaStream_t st = (cudaStream_t)stream;
     const int n_tiles = (int)ceil_div(rows, kTileM);
     const int64_t cslice = (int64_t)n_tiles * kTileM * kHid;
-    const BwdFn fn0 = bwd_kernel_for(planes, c_in == 1 ? 1 : kMaxC), fn1 = bwd_kernel_for(planes, 0);
-    if (int32_t rc = set_smem_attr((const void*)fn0, kBSmem)) return rc;
-    if (int32_t rc = set_smem_attr((const void*)fn1, kBSmem)) return rc;
-    CUtensorMap hp_map, h0_map;
-    STMGCN_REQUIRE(make_plane_map(&hp_map, hp, rows, (int64_t)n_layers * t_len * planes), STMGCN_ERR_STATE,
-                   "lstm16_step_bwd: cuTensorMapEncodeTiled failed (hp)");
+    const int l = layer;
+    const BwdFn fn = bwd_kernel_for(planes, l == 0 ? (c_in == 1 ? 1 : kMaxC) : 0);
+    if (int32_t rc = set_smem_attr((const void*)fn, kBSmem)) return rc;
+    Bwd16Params p;
+    memset(&p, 0, sizeof(p));
+    STMGCN_REQUIRE(make_plane_map(&p.maps[0], hp, rows, (int64_t)n_layers * t_len * planes), STMGCN_ERR_STATE,
+                   "lstm16_layer_bwd: cuTensorMapEncodeTiled failed (hp)");
     if (h0p != nullptr)
-        STMGCN_REQUIRE(make_plane_map(&h0_map, h0p, rows, (int64_t)n_layers * planes), STMGCN_ERR_STATE,
-                       "lstm16_step_bwd: cuTensorMapEncodeTiled failed (h0p)");
+        STMGCN_REQUIRE(make_plane_map(&p.maps[1], h0p, rows, (int64_t)n_layers * planes), STMGCN_ERR_STATE,
+                       "lstm16_layer_bwd: cuTensorMapEncodeTiled failed (h0p)");
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-    for (int l = n_layers - 1; l >= 0; --l) {
-        STMGCN_REQUIRE(wimg[l] && bias[l] && dbp[l], STMGCN_ERR_ARG, "lstm16_step_bwd: wimg/bias/dbp[%d] null", l);
-        Bwd16Params p;
-        memset(&p, 0, sizeof(p));
+    const bool top = (l == n_layers - 1);
+    p.zero_tile = (const uint8_t*)zero_tile;
+    p.wimg = (const uint8_t*)wimg;
+    p.bias = bias;
+    p.wih = (l == 0) ? wih_t : nullptr;
+    p.xo = xo;
+    p.sg = s_gate;
+    p.d_s = d_s;
+    p.c_in = c_in;
+    p.t_len = t_len;
+    p.n_steps = t_len;
+    p.b_inner = b_inner;
+    p.dh_rec = dh_rec;
+    p.dc = dc;
+    p.dbp = dbp;
+    p.dw_slice = dw_scratch;
+    p.rows = rows;
+    p.n_tiles = n_tiles;
+    for (int si = 0; si < t_len; ++si) {
+        const int t = t_len - 1 - si;
+        Bwd16Step& sp = p.steps[si];
         int ns = 0;
-        if (l > 0) {
-            p.amap[ns] = hp_map;
-            p.aslice[ns] = ((l - 1) * t_len + t) * planes;
+        if (l > 0) {                                               // K segment: h of the layer below at this step
+            sp.src[ns] = 0;
+            sp.slice[ns] = ((l - 1) * t_len + t) * planes;
             ++ns;
         }
-        if (t > 0) {
-            p.amap[ns] = hp_map;
-            p.aslice[ns] = (l * t_len + t - 1) * planes;
-            ++ns;
+        if (t > 0) {                                               // K segment: this layer's h of the previous step
+            sp.src[ns] = 0;
+            sp.slice[ns] = (l * t_len + t - 1) * planes;
         } else if (h0p != nullptr) {
-            p.amap[ns] = h0_map;
-            p.aslice[ns] = l * planes;
-            ++ns;
-        }
-        p.nseg = ns;
-        p.layer0 = (l == 0) ? 1 : 0;
-        p.wimg = (const uint8_t*)wimg[l];
-        p.bias = bias[l];
-        p.wih = (l == 0) ? wih_t : nullptr;
-        p.xo = xo;
-        p.sg = s_gate;
-        p.d_s = d_s;
-        p.c_in = c_in;
-        p.t = t;
-        p.t_len = t_len;
-        p.b_inner = b_inner;
-        p.c_prev = t > 0 ? cs + (int64_t)(l * t_len + t - 1) * cslice : (c0 ? c0 + (int64_t)l * cslice : nullptr);
-        p.dh_in = (l == n_layers - 1) ? (t == t_len - 1 ? d_top : nullptr) : dx_work;
-        p.dh_rec = dh_rec + (int64_t)l * cslice;
-        p.dc = dc + (int64_t)l * cslice;
-        p.dx_out = l > 0 ? dx_work : nullptr;
-        p.first = (t == t_len - 1) ? 1 : 0;
-        p.store_dh = (t > 0 || h0p != nullptr) ? 1 : 0;
-        p.dbp = dbp[l];
-        p.dw_slice = dw_scratch + (size_t)l * grid * (kTileM * kGateCols);
-        p.dw_first = (t == t_len - 1) ? 1 : 0;
-        if (l > 0) {
-            p.flush_lo = 1;
-            p.flush_hi = (ns == 2) ? 1 : 0;
+            sp.src[ns] = 1;
+            sp.slice[ns] = l * planes;
         } else {
-            p.flush_lo = (ns == 1) ? 1 : 0;
-            p.flush_hi = 1;
+            sp.src[ns] = 2;                                        // zeros (STMGCN.py:53-57)
+            sp.slice[ns] = 0;
         }
-        p.rows = rows;
-        p.n_tiles = n_tiles;
-        (l == 0 ? fn0 : fn1)<<<grid, kBThreads, kBSmem, st>>>(p);
-        count_launch();
-        if (int32_t rc = check_launch("lstm16_bwd")) return rc;
+        sp.t = t;
+        sp.first = (t == t_len - 1) ? 1 : 0;
+        sp.store_dh = (t > 0 || h0p != nullptr) ? 1 : 0;
+        sp.c_prev = t > 0 ? cs + (int64_t)(l * t_len + t - 1) * cslice : (c0 ? c0 + (int64_t)l * cslice : nullptr);
+        sp.dh_in = top ? (t == t_len - 1 ? dh_in : nullptr) : dh_in + (int64_t)t * cslice;
+        sp.dx_out = l > 0 ? dx_out + (int64_t)t * cslice : nullptr;
     }
-    return 0;
+    fn<<<grid, kBThreads, kBSmem, st>>>(p);
+    count_launch();
+    return check_launch("lstm16_layer_bwd");
 }
 
 extern "C" int32_t stmgcn_lstm16_wgrad_reduce(int32_t layer, int32_t c_in, int32_t n_slices, const float* slices,

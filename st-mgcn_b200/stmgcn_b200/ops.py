@@ -475,9 +475,21 @@ def _lstm16_forward(xo, s_gate, h0c, c0c, n_layers, want_state, weights, planes,
     return h_top.view(n, b, 64), h_n, c_n, tape
 
 
+_ZERO_TILES: dict = {}
+
+
+def _zero_tile(dev: torch.device) -> torch.Tensor:
+    """16 KB of zeros per device: the h_prev operand tile at t = 0 without an initial state."""
+    key = str(dev)
+    if key not in _ZERO_TILES:
+        _ZERO_TILES[key] = torch.zeros(128 * 64, device=dev, dtype=torch.bfloat16)
+    return _ZERO_TILES[key]
+
+
 def _lstm16_backward(xo, s_gate, tape, n_layers, planes, d_top):
-    """BPTT of the bf16-plane path: one fused kernel per layer-step (gate recompute + pointwise + data gradient + weight
-    gradient, stmgcn_lstm16_step_bwd), then one reduction per layer.  Returns (d_s, [native nn.LSTM gradients])."""
+    """BPTT of the bf16-plane path: ONE fused launch per layer over all timesteps (gate recompute + pointwise + data
+    gradient + weight gradient, stmgcn_lstm16_layer_bwd), layers top-down, then one reduction per layer.
+    Returns (d_s, [native nn.LSTM gradients])."""
     n, b, t_len, c_in = xo.shape
     rows = n * b
     dev = xo.device
@@ -485,21 +497,25 @@ def _lstm16_backward(xo, s_gate, tape, n_layers, planes, d_top):
     img = tape["img"]
     torch.cuda.current_stream().wait_event(img["event"]) if "event" in img else None
     d_top_b = to_blocked(_f32c(d_top).view(rows, 64))
-    dh_rec = torch.empty((n_layers, rows_pad, 64), device=dev, dtype=torch.float32)
-    dc = torch.empty((n_layers, rows_pad, 64), device=dev, dtype=torch.float32)
-    dx_work = torch.empty((rows_pad, 64), device=dev, dtype=torch.float32)
+    dh_rec = torch.empty((rows_pad, 64), device=dev, dtype=torch.float32)
+    dc = torch.empty((rows_pad, 64), device=dev, dtype=torch.float32)
+    # dx of a layer for every timestep: written by layer l, read by layer l - 1 (two buffers ping-pong down the stack)
+    dx_bufs = [torch.empty((t_len, rows_pad, 64), device=dev, dtype=torch.float32) for _ in range(min(2, n_layers - 1))]
     d_s = torch.zeros((b, t_len), device=dev, dtype=torch.float32)
     dbp = torch.zeros((n_layers, 256), device=dev, dtype=torch.float32)
     grid = int(L.stmgcn_lstm16_grid(rows))
     scratch = torch.empty((n_layers, grid, 128 * 256), device=dev, dtype=torch.float32)
-    dbp_arr = _lib.ptr_array([dbp[l].data_ptr() for l in range(n_layers)])
+    zero = _zero_tile(dev)
     st = _stream()
-    for t in range(t_len - 1, -1, -1):
-        _lib.check(L.stmgcn_lstm16_step_bwd(t, t_len, n_layers, rows, c_in, b, planes, xo.data_ptr(), s_gate.data_ptr(),
-                                            img["wimg_arr"], img["bias_arr"], img["wih_t"].data_ptr(), _p(tape["h0p"]),
-                                            _p(tape["c0b"]), tape["hp"].data_ptr(), tape["cs"].data_ptr(),
-                                            d_top_b.data_ptr(), dh_rec.data_ptr(), dc.data_ptr(), dx_work.data_ptr(),
-                                            d_s.data_ptr(), dbp_arr, scratch.data_ptr(), st), "lstm16_step_bwd")
+    dh_in = d_top_b
+    for l in range(n_layers - 1, -1, -1):
+        dx_out = dx_bufs[(n_layers - 1 - l) % 2] if l > 0 else None
+        _lib.check(L.stmgcn_lstm16_layer_bwd(l, t_len, n_layers, rows, c_in, b, planes, xo.data_ptr(), s_gate.data_ptr(),
+                                             img["wimg"][l].data_ptr(), img["bias"][l].data_ptr(), img["wih_t"].data_ptr(),
+                                             _p(tape["h0p"]), _p(tape["c0b"]), tape["hp"].data_ptr(), tape["cs"].data_ptr(),
+                                             dh_in.data_ptr(), _p(dx_out), dh_rec.data_ptr(), dc.data_ptr(), d_s.data_ptr(),
+                                             dbp[l].data_ptr(), scratch[l].data_ptr(), zero.data_ptr(), st), "lstm16_layer_bwd")
+        dh_in = dx_out
     grads = []
     for l in range(n_layers):
         in_l = c_in if l == 0 else 64
@@ -522,7 +538,7 @@ class SharedLSTM(torch.autograd.Function):
     Returns (h_top, h_n (L,R,H), c_n (L,R,H)); the last two are not differentiable.
 
     Two kernel families (include/stmgcn_b200.h):
-    * H = 64, C <= 4 (the reference's configuration, Main.py:62) and ``lstm_path() == "tc"``: the tcgen05 bf16-plane
+    * H = 64, C <= 4, T <= 64 (the reference's configuration, Main.py:62) and ``lstm_path() == "tc"``: the tcgen05 bf16-plane
       kernels of lstm16.cu -- tape = hidden-state planes + cell state, no gate tape, fused recompute backward;
     * anything else, or ``lstm_path() == "fma"``: the exact-fp32 CUDA-core kernels of lstm.cu with their own tape
       (hs, cs, gates); their backward overwrites the gate tape in place, so it can run only once per forward.
@@ -540,7 +556,7 @@ class SharedLSTM(torch.autograd.Function):
         c0c = _f32c(c0) if c0 is not None else None
         need_grad = any(ctx.needs_input_grad)
         ctx.dims = (n, b, t_len, c_in, n_layers, hid)
-        if hid == 64 and lstm_path() == "tc" and c_in <= 4:
+        if hid == 64 and lstm_path() == "tc" and c_in <= 4 and t_len <= 64:
             planes = lstm_planes()
             h_top, h_n, c_n, tape = _lstm16_forward(xo, s_gate, h0c, c0c, n_layers, want_state, weights, planes, need_grad)
             ctx.mark_non_differentiable(h_n, c_n)
