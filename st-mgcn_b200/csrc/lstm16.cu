@@ -492,7 +492,8 @@ struct Bwd16Params {
     float* dh_rec;             // blocked, in (unless first) / out, in place through the steps
     float* dc;                 // blocked, in (unless first) / out, in place through the steps
     float* dbp;                // (256) +=  gate-interleaved bias gradient
-    float* dw_slice;           // gridDim.x slices of 128*256 floats (accumulator register layout), written once
+    float* dw_slice;           // gridDim.x slices of 128*256 floats (accumulator register layout)
+    int dw_first;              // 1: first launch of this layer: slices are written, not accumulated
     int64_t rows;
     int n_tiles;
     Bwd16Step steps[kBMaxSteps];   // in execution order: steps[0] is t = T-1
@@ -1079,7 +1080,10 @@ __global__ void __launch_bounds__(kBThreads, 1) lstm16_bwd_kernel(const __grid_c
                     float4* dst = reinterpret_cast<float4*>(slice + ((size_t)((part * 4 + j) * 4 + e) * kTileM + m) * 4);
                     float4 acc = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
                                              __uint_as_float(v[4 * e + 3]));
-                    *dst = acc;                  // (one launch per layer: the slice is written once, never accumulated)
+                    // later launches of the layer add with a fire-and-forget vector reduction (the slice is private to this
+                    // CTA: no contention, no read latency at the end of the launch)
+                    if (p.dw_first) *dst = acc;
+                    else red_add_f32x4(dst, acc);
                 }
             }
         }
@@ -1305,7 +1309,6 @@ extern "C" int32_t stmgcn_lstm16_layer_bwd(int32_t layer, int32_t t_len, int32_t
     p.d_s = d_s;
     p.c_in = c_in;
     p.t_len = t_len;
-    p.n_steps = t_len;
     p.b_inner = b_inner;
     p.dh_rec = dh_rec;
     p.dc = dc;
@@ -1313,35 +1316,50 @@ extern "C" int32_t stmgcn_lstm16_layer_bwd(int32_t layer, int32_t t_len, int32_t
     p.dw_slice = dw_scratch;
     p.rows = rows;
     p.n_tiles = n_tiles;
-    for (int si = 0; si < t_len; ++si) {
-        const int t = t_len - 1 - si;
-        Bwd16Step& sp = p.steps[si];
-        int ns = 0;
-        if (l > 0) {                                               // K segment: h of the layer below at this step
-            sp.src[ns] = 0;
-            sp.slice[ns] = ((l - 1) * t_len + t) * planes;
-            ++ns;
+    // Steps per launch: the weight-gradient accumulator of a CTA lives in TMEM for the whole launch, and the tensor core's fp32
+    // accumulation loses precision with the length of the chain (all T steps of cfg5's 7 tiles per CTA = 21.5 k rows in one
+    // chain put 1.3e-4 into the LSTM weight gradients, measured; per-step launches, 1.8 k rows: 1.4e-5).  A launch therefore
+    // covers at most kMaxChainItems (step, tile) items per CTA; the slices are summed across launches in fp32 memory.
+    constexpr int kMaxChainItems = 48;                             // 6144 rows per accumulation chain
+    const int tiles_per_cta = (int)ceil_div(n_tiles, grid);
+    int steps_per_launch = kMaxChainItems / tiles_per_cta;
+    if (steps_per_launch < 1) steps_per_launch = 1;
+    for (int s0 = 0; s0 < t_len; s0 += steps_per_launch) {
+        const int ns_launch = (t_len - s0 < steps_per_launch) ? (t_len - s0) : steps_per_launch;
+        p.n_steps = ns_launch;
+        p.dw_first = (s0 == 0) ? 1 : 0;
+        for (int sj = 0; sj < ns_launch; ++sj) {
+            const int si = s0 + sj;
+            const int t = t_len - 1 - si;
+            Bwd16Step& sp = p.steps[sj];
+            int ns = 0;
+            if (l > 0) {                                               // K segment: h of the layer below at this step
+                sp.src[ns] = 0;
+                sp.slice[ns] = ((l - 1) * t_len + t) * planes;
+                ++ns;
+            }
+            if (t > 0) {                                               // K segment: this layer's h of the previous step
+                sp.src[ns] = 0;
+                sp.slice[ns] = (l * t_len + t - 1) * planes;
+            } else if (h0p != nullptr) {
+                sp.src[ns] = 1;
+                sp.slice[ns] = l * planes;
+            } else {
+                sp.src[ns] = 2;                                        // zeros (STMGCN.py:53-57)
+                sp.slice[ns] = 0;
+            }
+            sp.t = t;
+            sp.first = (t == t_len - 1) ? 1 : 0;
+            sp.store_dh = (t > 0 || h0p != nullptr) ? 1 : 0;
+            sp.c_prev = t > 0 ? cs + (int64_t)(l * t_len + t - 1) * cslice : (c0 ? c0 + (int64_t)l * cslice : nullptr);
+            sp.dh_in = top ? (t == t_len - 1 ? dh_in : nullptr) : dh_in + (int64_t)t * cslice;
+            sp.dx_out = l > 0 ? dx_out + (int64_t)t * cslice : nullptr;
         }
-        if (t > 0) {                                               // K segment: this layer's h of the previous step
-            sp.src[ns] = 0;
-            sp.slice[ns] = (l * t_len + t - 1) * planes;
-        } else if (h0p != nullptr) {
-            sp.src[ns] = 1;
-            sp.slice[ns] = l * planes;
-        } else {
-            sp.src[ns] = 2;                                        // zeros (STMGCN.py:53-57)
-            sp.slice[ns] = 0;
-        }
-        sp.t = t;
-        sp.first = (t == t_len - 1) ? 1 : 0;
-        sp.store_dh = (t > 0 || h0p != nullptr) ? 1 : 0;
-        sp.c_prev = t > 0 ? cs + (int64_t)(l * t_len + t - 1) * cslice : (c0 ? c0 + (int64_t)l * cslice : nullptr);
-        sp.dh_in = top ? (t == t_len - 1 ? dh_in : nullptr) : dh_in + (int64_t)t * cslice;
-        sp.dx_out = l > 0 ? dx_out + (int64_t)t * cslice : nullptr;
+        fn<<<grid, kBThreads, kBSmem, st>>>(p);
+        count_launch();
+        if (int32_t rc = check_launch("lstm16_layer_bwd")) return rc;
     }
-    fn<<<grid, kBThreads, kBSmem, st>>>(p);
-    count_launch();
-    return check_launch("lstm16_layer_bwd");
+    return 0;
 }
 
 extern "C" int32_t stmgcn_lstm16_wgrad_reduce(int32_t layer, int32_t c_in, int32_t n_slices, const float* slices,
