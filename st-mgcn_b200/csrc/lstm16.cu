@@ -418,7 +418,8 @@ __global__ void lstm16_pack_kernel(const float* __restrict__ w_ih, const float* 
 
 
 // =====================================================================================================
-// backward: gate recompute + BPTT pointwise + data gradient + weight gradient in ONE kernel per layer-step
+// backward: gate recompute + BPTT pointwise + data gradient + weight gradient in ONE kernel, time-fused per layer
+// (a launch = one layer x a run of timesteps, see Bwd16Params; "tile" below = one (step, tile) work item)
 // =====================================================================================================
 // Per 128-row tile, the 256 gate columns are processed as four chunks of 64 (16 units x i,f,g,o):
 //   R_c : recompute the chunk's pre-activations  G_c[128 x 64] = [h_below | h_prev] . Wp[:, chunk]     (TMEM, 64 columns)
