@@ -37,6 +37,24 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib.stmgcn_launch_count() >= 0
 
 
+def test_c_abi_argument_errors_come_back_as_codes_with_a_message():
+    """The C entry points validate their arguments before touching CUDA: a bad call returns a negative code and
+    stmgcn_last_error() explains it (no GPU needed).  Covers the entries added in ABI 3."""
+    import ctypes
+    from stmgcn_b200 import _lib
+    lib = _lib.lib
+    null = ctypes.c_void_p(0)
+    # time-fused LSTM backward: null workspaces
+    rc = lib.stmgcn_lstm16_layer_bwd(0, 12, 3, 128, 1, 8, 2, *([null] * 18))
+    assert rc < 0 and b"lstm16_layer_bwd" in lib.stmgcn_last_error()
+    # bf16 gather step: null graph; conversion: count not a multiple of 8
+    rc = lib.stmgcn_cheb_spmm_step16(null, 0, 1.0, null, 0.0, null, 0.0, null, null, null, 64, null)
+    assert rc < 0 and b"cheb_spmm_step16" in lib.stmgcn_last_error()
+    buf = (ctypes.c_float * 16)()
+    rc = lib.stmgcn_to_bf16(ctypes.addressof(buf), ctypes.addressof(buf), 12, null)
+    assert rc < 0 and b"multiple of 8" in lib.stmgcn_last_error()
+
+
 def test_no_cpu_fallback_is_loud():
     import GCN
     from stmgcn_b200 import ops

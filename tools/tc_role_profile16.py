@@ -59,7 +59,7 @@ def main():
         h_top, _, _ = ops.SharedLSTM.apply(xo, s, None, None, lyr, hid, False, *ws)
         report(f"forward (36 launches), iteration {it}")
         h_top.backward(d_top)
-        report(f"backward (36 launches + 3 reductions), iteration {it}")
+        report(f"backward (time-fused launches + 3 reductions), iteration {it}")
 
 
 if __name__ == "__main__":
