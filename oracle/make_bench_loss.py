@@ -7,7 +7,8 @@ For those inputs the MSE loss of the first step is a constant; this script compu
 it in ``tests/golden/bench_loss.json``.  bench.py compares the loss its timed step produces with the stored value, so a
 kernel that is fast but wrong at the BENCHMARKED size cannot print a number.
 
-    python oracle/make_bench_loss.py [workload ...]      (default: cfg3 ranks 0-7, cfg2 rank 0)
+    python oracle/make_bench_loss.py [workload ...]      (default: cfg3 ranks 0-7, cfg2 rank 0, cfg1 rank 0; workloads with
+                                                         identical shapes -- cfg4 = cfg3 in bf16 -- share the values)
 """
 from __future__ import annotations
 
@@ -65,6 +66,27 @@ def main():
         print(f"{key}: loss {table[key]:.9f}  ({time.time() - t0:.0f}s)", flush=True)
         with open(OUT, "w") as fh:
             json.dump(table, fh, indent=1, sort_keys=True)
+    alias_identical_workloads(table)
+    with open(OUT, "w") as fh:
+        json.dump(table, fh, indent=1, sort_keys=True)
+
+
+def alias_identical_workloads(table):
+    """The reference loss is a pure function of the workload's SHAPE fields, the batch and the rank (see reference_loss):
+    a workload that differs from another only in name and dtype label (cfg4 = cfg3's shapes quoted in bf16) has the same
+    fp64 losses.  Copy them instead of recomputing (bench.py applies the tolerance of the arithmetic it runs)."""
+    import dataclasses
+    from stmgcn_b200 import synth
+
+    def shape_of(w):
+        d = dataclasses.asdict(w)
+        d.pop("name"), d.pop("dtype")
+        return d
+    for key in list(table):
+        name, rest = key.split("/", 1)
+        for other, w in synth.WORKLOADS.items():
+            if other != name and name in synth.WORKLOADS and shape_of(w) == shape_of(synth.WORKLOADS[name]):
+                table.setdefault(f"{other}/{rest}", table[key])
 
 
 if __name__ == "__main__":
